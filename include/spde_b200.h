@@ -1,0 +1,158 @@
+/* spde_b200.h -- C ABI of the B200-native SPDE precision-and-likelihood hot path.
+ *
+ * One shared library, `spdepy_b200/csrc/libspde_b200.so`, built by nvcc for sm_100a.  Plain C
+ * types only: ints, doubles, raw device/host pointers and a `void*` CUDA stream.  Every entry
+ * point returns an int status (SPDE_OK or an SPDE_ERR_* code; `spde_last_error()` gives text).
+ * All `d_*` pointers are DEVICE pointers owned by the caller; the library owns only the plan and
+ * its internal workspaces.  Calls are stream-ordered on the stream passed in (NULL = default).
+ *
+ * What each group replaces in the reference (berild/spdepy; paths relative to /root/reference):
+ *
+ *   stencils      the ctypes FFI `AH_new/AH_Row/AH_Col/AH_Val/AH_delete` and `Aw_*`
+ *                 (src/spdepy/spdes/ccode/AcH_2D_b1.cpp:170-185, AH_2D_b1.cpp:154-169,
+ *                 Acw_2D_b1.cpp:117-132, Aw_2D_b1.cpp:136-151) and the Python wrappers `Ah()/Aw()`
+ *                 (src/spdepy/spdes/advection_diffusion2D.py:226-260)
+ *   assembly      the scipy.sparse SpGEMM / bmat block stacking of `makeQ`
+ *                 (advection_diffusion2D.py:101-116, whittle_matern_anisotropic2D.py:69-73)
+ *   plan/factor   `sksparse.cholmod.cholesky(Q)` (advection_diffusion2D.py:117,193; model.py:79,125)
+ *   solves        `Factor.solve_A / solve_Lt / apply_Pt / logdet`
+ *                 (advection_diffusion2D.py:194-202, model.py:80,126)
+ *   selinv        the R/INLA `inla.run -m qinv` subprocess (src/spdepy/rqinv.R:18-70, model.py:89-118)
+ *   likelihood    the NumPy reductions of `logLike` (advection_diffusion2D.py:198-208)
+ *
+ * Slot layouts (all slot-major, i.e. `a[slot*Ns + cell]`, so a warp reads/writes 256 contiguous
+ * bytes per slot):
+ *   A9   operator stencil, slot = (dj+1)*3 + (di+1), dj,di in {-1,0,1}: value of row `cell` at
+ *        column `cell + dj*M + di` (wrapped for bc=2).  Slots whose neighbour is outside the
+ *        mesh hold 0; Neumann duplicates (AcH_2D_b1.cpp:71-118) are already folded.
+ *   Q25  spatial precision row, slot = (dj+2)*5 + (di+2), dj,di in {-2..2}.
+ *   Q43  space-time precision row of node (cell,t): slots 0..8 = 3x3 block to t-1, 9..33 = 5x5
+ *        block in t, 34..42 = 3x3 block to t+1; address `q[slot*n + t*Ns + cell]`.
+ */
+#ifndef SPDE_B200_H
+#define SPDE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPDE_OK 0
+#define SPDE_ERR_NOT_SPD 1   /* a pivot was <= 0 or NaN; see spde_factor_info */
+#define SPDE_ERR_OOM 2
+#define SPDE_ERR_ARG 3
+#define SPDE_ERR_CUDA 4
+
+typedef struct spde_plan spde_plan;
+
+int spde_abi_version(void);
+const char *spde_last_error(void);
+
+/* ------------------------------------------------------------------ stencils (K2) */
+
+/* 9-point finite-volume stencil of div(H grad).  `face`=0: d_H holds one 2x2 tensor (4 doubles,
+ * row-major) [AcH_2D_b{1,3}.cpp]; `face`=1: d_H holds H[cell][4 faces W,E,S,N][2][2]
+ * [AH_2D_b{1,2,3}.cpp].  Output d_ah9 in the A9 layout.  bc: 1 Neumann, 2 periodic, 3 Dirichlet.
+ * bc=2 with face=0 is rejected: the reference returns NaN there (AcH_2D_b2.cpp:105). */
+int spde_ah_stencil(int M, int N, int bc, double hx, double hy, const double *d_H, int face,
+                    double *d_ah9, void *stream);
+
+/* 5-point upwind advection stencil.  `face`=0: d_G = (wx, wy) [Acw_2D_b*.cpp]; `face`=1:
+ * d_G / d_dG hold face-normal velocities [cell][E,N,W,S] [Aw_2D_b*.cpp] (d_dG may be NULL when
+ * diff==3).  diff: 1 = d/dwx, 2 = d/dwy, 3 = value.  `nan_to_zero` applies the filter of
+ * var_advection_var_diffusion2D.py:255.  Output d_aw9 in the A9 layout (corner slots 0). */
+int spde_aw_stencil(int M, int N, int bc, double hx, double hy, const double *d_G, const double *d_dG,
+                    int face, int diff, int nan_to_zero, double *d_aw9, void *stream);
+
+/* A = f(V, kappa, ah, aw, dt) in the reference's operation order.
+ * flavour 0: V*kappa - ah                         (whittle_matern2D.py:69)
+ * flavour 1: V + (V*kappa)*dt - ah*dt + aw*dt     (advection_diffusion2D.py:104)
+ * flavour 2: V + ((V*kappa - ah) + aw)*dt         (var_advection_var_diffusion2D.py:103)
+ * flavour 3: -(ah*dt)   flavour 4: aw*dt   flavour 5: -ah   (derivative directions)
+ * kvar=0: d_kappa points at one double; kvar=1: one per cell. d_aw9 may be NULL. */
+int spde_combine_A(int Ns, int flavour, double V, double dt, const double *d_kappa, int kvar,
+                   const double *d_ah9, const double *d_aw9, double *d_A9, void *stream);
+
+/* ------------------------------------------------------------------ assembly (K3) */
+
+/* out25 = A^T D A on the 5x5 pattern, D = 1/V (mode 0, whittle_matern2D.py:70) or
+ * D = kappa^2/V evaluated as ((a*iV)*Qs)*iV with Qs = ((V k)*iV)*(V k) (mode 1,
+ * advection_diffusion2D.py:103,114).  Inner index accumulated in ascending cell order. */
+int spde_atda(int M, int N, int bc, const double *d_A9, const double *d_kappa, int kvar, double V,
+              int mode, double *d_out25, void *stream);
+
+/* Block-tridiagonal space-time precision (advection_diffusion2D.py:112-116) into the Q43 layout.
+ * d_Q0_25: initial-field precision (Q25 layout); divide=0: (1/(dt*sigma))*x, 1: x/(dt*sigma). */
+int spde_fill_spacetime(int M, int N, int T, int bc, const double *d_AtDA25, const double *d_A9,
+                        const double *d_kappa, int kvar, double V, const double *d_Q0_25,
+                        double sigma, double dt, int divide, double *d_Q43, void *stream);
+
+/* ------------------------------------------------------------------ symbolic plan (host, once per mesh) */
+
+/* Geometric nested dissection + elimination tree + supernodes + level schedule + kernel task
+ * lists for the pattern of an M x N (x T) mesh (T=1: Q25 pattern, T>1: Q43 pattern).
+ * Replaces CHOLMOD's analyse phase; the permutation is exposed by spde_plan_perm. */
+int spde_plan_create(int M, int N, int T, int bc, int max_rhs, spde_plan **out);
+void spde_plan_destroy(spde_plan *p);
+/* info ids: 0 n, 1 nsuper, 2 nnz(L) stored, 3 flops sum cc^2 (as double bits via spde_plan_info_d),
+ * 4 factor bytes, 5 arena bytes, 6 nlevels, 7 max front, 8 n launches (factor) */
+int64_t spde_plan_info(const spde_plan *p, int what);
+double spde_plan_info_d(const spde_plan *p, int what);
+int spde_plan_perm(const spde_plan *p, int32_t *h_perm /* n, new -> old */);
+/* host copies of the supernodal structure, for tests / the CPU restatement in oracle/ */
+int spde_plan_supernodes(const spde_plan *p, int32_t *h_first /* nsuper+1 */, int64_t *h_rowptr /* nsuper+1 */,
+                         int32_t *h_rows /* rowptr[nsuper] */, int32_t *h_parent /* nsuper */);
+
+/* Raw host copy of a schedule (prog 0 factor, 1 forward solve, 2 backward solve, 3 selected inverse;
+ * what 0 launches, 1 GEMM tasks, 2 tiles, 3 POTRF, 4 extend-add, 5 gather, 6 W^T W tasks) or of the
+ * storage layout (prog 4; what 0 sizes, 1 scatter map, 2 candidate slots, 3 diagonal positions,
+ * 4 rows|relative indices, 5 extraction entries, 6 extraction depth pointers, 7 column counts).
+ * Pass h_out=NULL to query the count and element size.  Test / inspection interface. */
+int spde_plan_export(spde_plan *p, int prog, int k, int what, void *h_out, int64_t *count, int *elem_size);
+
+/* ------------------------------------------------------------------ numeric factorisation (K4,K5,K6) */
+
+/* L L^T = P (Q + tau*diag(d_cnt)) P^T.  d_Q in Q25/Q43 layout (only the lower-triangle slots of
+ * the original ordering are read, as CHOLMOD does); d_cnt (n doubles, may be NULL) is the diagonal
+ * of S^T S (advection_diffusion2D.py:192).  `which` selects one of two factor stores (0: Q, 1: Q_c). */
+int spde_factorize(spde_plan *p, int which, const double *d_Q, const double *d_cnt, double tau, void *stream);
+int spde_factor_info(spde_plan *p, int which, int *h_status, int *h_bad_column);
+int spde_logdet(spde_plan *p, int which, double *h_logdet, void *stream);
+
+/* ------------------------------------------------------------------ solves (K7) */
+/* X is n x k, ROW-major on the device (node-major: the k values of a node are contiguous), in the
+ * ORIGINAL node ordering; solved in place.  mode 0: A x = b (solve_A); 1: L^T (P x) = b then P^T
+ * (solve_Lt + apply_Pt, model.py:80); 2: L y = P b (solve_L + apply_P). */
+int spde_solve(spde_plan *p, int which, int mode, double *d_X, int k, void *stream);
+
+/* ------------------------------------------------------------------ selected inverse (K10) */
+/* Takahashi recursion on the supernodal structure; writes Z = (L L^T)^-1 restricted to the
+ * pattern of Q into d_Zq (same Q25/Q43 layout, all stored slots filled symmetrically). */
+int spde_selinv(spde_plan *p, int which, double *d_Zq, void *stream);
+
+/* ------------------------------------------------------------------ likelihood / gradient reductions (K8,K9,K11) */
+/* y = Q x for k right-hand sides (x, y row-major n x k): stencil apply, no index arrays. */
+int spde_q_apply(int M, int N, int T, int bc, const double *d_Q, const double *d_X, int k, double *d_Y, void *stream);
+/* h_out[0] = sum(X .* Y) over n*k entries (deterministic two-stage reduction). */
+int spde_dot(const double *d_X, const double *d_Y, int64_t len, double *h_out, void *stream);
+/* W[slot,node] (+)= alpha * sum_p X[node,p] * Y[nbr(node,slot),p]  (sampled dense-dense product on the
+ * pattern of Q; the Hutchinson weights of advection_diffusion2D.py:204-206). */
+int spde_sddmm(int M, int N, int T, int bc, const double *d_X, const double *d_Y, int k, double alpha,
+               int accumulate, double *d_W, void *stream);
+/* Adjoint of the assembly (transpose of spde_atda / spde_fill_spacetime): given weights W on the
+ * pattern of Q, d sum(W .* Q) / d A9 (d_GA9, A9 layout), / d Qs per cell (d_Gq, Ns; Qs = kappa^2 V,
+ * advection_diffusion2D.py:103) and / d Q0 (d_GQ0_25).  timed=0: W, Q in the Q25 layout and only
+ * d_GA9 is produced.  d_work: 44*Ns doubles of scratch (timed only).  With these, the trace
+ * sum(W .* dQ_i) of every parameter i (advection_diffusion2D.py:119-182, 204-206) is a dot
+ * product with that parameter's stencil direction dA_i instead of an n x n sparse matrix. */
+int spde_assembly_adjoint(int M, int N, int T, int bc, const double *d_W, const double *d_A9,
+                          const double *d_kappa, int kvar, double V, double sigma, double dt, int timed,
+                          double *d_work, double *d_GA9, double *d_Gq, double *d_GQ0_25, void *stream);
+/* d_out[c] = sum_r B[r,c] * u[r], B row-major rows x cols (spline-basis chain rule, evalB/evalBH). */
+int spde_gemv_t(const double *d_B, const double *d_u, int rows, int cols, double *d_out, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,220 @@
+// gemm.cuh -- grouped FP64 tensor-core GEMM: the one dense contraction on the hot path.
+//
+// Blackwell's tcgen05/UMMA has no FP64 kind (SURVEY.md finding 10); FP64 tensor-core math on
+// sm_100a is `mma.sync.aligned.m8n8k4.f64` (SASS DMMA.8x8x4).  Every dense block operation of the
+// supernodal factorisation, the triangular solves and the Takahashi recursion is expressed as a
+// *task* `C (op)= +-A*B` on column-major operands and executed by this kernel:
+//   - one launch covers all tasks of a level (grouped GEMM): grid = total number of C tiles,
+//     a host-built tile table maps blockIdx.x -> (task, tile row, tile col);
+//   - operand tiles are staged global -> shared with 16-byte cp.async (LDGSTS) in a 3-stage
+//     ring; the +4 double row padding makes the DMMA fragment loads bank-conflict free;
+//   - each warp owns a WMxWN block of 8x8 accumulator tiles held in registers.
+// Variants (template): A/B stored with the tile dimension contiguous ("N") or with K contiguous
+// ("T"); runtime flags select sign, overwrite, lower-triangle masking, a column gather on A
+// (back substitution reads scattered rows of X) and an atomic column scatter on C (forward
+// substitution updates scattered rows of X).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace spde {
+
+enum : int {
+    GF_LOWER = 1 << 9,      // only elements with (row >= col) of C are written, tiles above skipped
+    GF_BETA0 = 1 << 10,     // C = +-A*B instead of C += +-A*B
+    GF_NEG = 1 << 11,       // C -= A*B
+    GF_ATOMIC = 1 << 12,    // atomicAdd into C (several tasks may hit the same column)
+    GF_GATHER_A = 1 << 13,  // column kk of A is column idx[aidx+kk] of the A space
+    GF_SCATTER_C = 1 << 14, // column j of C is column idx[cidx+j] of the C space
+    GF_UPPER_MIRROR = 1 << 15, // also write the transposed block at c2 (keeps selected-inverse fronts symmetric)
+};
+
+struct GemmTask {
+    long long a, b, c;   // element offsets into the operand spaces
+    long long c2;        // origin of the mirrored block (GF_UPPER_MIRROR): element (r,c) also goes to c2 + c + r*ldc
+    int lda, ldb, ldc;
+    int M, N, K;
+    int flags;           // bits 0-2 A space, 3-5 B space, 6-8 C space, then GF_*
+    int aidx, cidx;      // offsets into the index array
+    int pad;
+};
+
+struct GemmSpaces {
+    double *base[8];
+    const int *idx;
+};
+
+struct TileRef { int task, ti, tj, pad; };
+
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem, int src_bytes)
+{
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+__device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(d0), "+d"(d1)
+                 : "d"(a), "d"(b));
+}
+
+constexpr int GEMM_BK = 16;
+constexpr int GEMM_STAGES = 3;
+
+template <int BM, int BN>
+constexpr int gemm_smem_bytes()
+{
+    // worst case of the two layouts per operand
+    constexpr int a = (BM + 4) * GEMM_BK > BM * (GEMM_BK + 4) ? (BM + 4) * GEMM_BK : BM * (GEMM_BK + 4);
+    constexpr int b = (BN + 4) * GEMM_BK > BN * (GEMM_BK + 4) ? (BN + 4) * GEMM_BK : BN * (GEMM_BK + 4);
+    return GEMM_STAGES * (a + b) * 8;
+}
+
+// Load one BT x BK operand tile into shared memory.
+//  KMAJ=false: element (i,kk) at g[i + col(kk)*ld]   -> smem[kk][BT+4]
+//  KMAJ=true : element (i,kk) at g[kk + i*ld]        -> smem[i][BK+4]
+template <int BT, bool KMAJ, int NT>
+__device__ __forceinline__ void load_tile(double *smem, const double *g, int ld, int rows, int k0, int K,
+                                          const int *gather, int tid)
+{
+    if (!KMAJ) {
+        constexpr int CH = BT / 2;               // 16-byte chunks per k-column
+        for (int id = tid; id < CH * GEMM_BK; id += NT) {
+            const int kk = id / CH, ic = (id % CH) * 2;
+            const int kg = k0 + kk;
+            int bytes = 0;
+            const double *src = g;
+            if (kg < K && ic < rows) {
+                const long long col = gather ? (long long)gather[kg] : (long long)kg;
+                src = g + ic + col * ld;
+                bytes = (rows - ic >= 2) ? 16 : 8;
+            }
+            cp_async16(smem + kk * (BT + 4) + ic, src, bytes);
+        }
+    } else {
+        constexpr int CH = GEMM_BK / 2;          // 16-byte chunks per row
+        for (int id = tid; id < CH * BT; id += NT) {
+            const int i = id / CH, kc = (id % CH) * 2;
+            const int kg = k0 + kc;
+            int bytes = 0;
+            const double *src = g;
+            if (i < rows && kg < K) {
+                src = g + kg + (long long)i * ld;
+                bytes = (K - kg >= 2) ? 16 : 8;
+            }
+            cp_async16(smem + i * (GEMM_BK + 4) + kc, src, bytes);
+        }
+    }
+}
+
+template <int BM, int BN, int WARPS_M, int WARPS_N, bool A_KMAJ, bool B_KMAJ>
+__global__ void __launch_bounds__(WARPS_M *WARPS_N * 32)
+k_gemm_grouped(const GemmTask *__restrict__ tasks, const TileRef *__restrict__ tiles, GemmSpaces sp)
+{
+    constexpr int NT = WARPS_M * WARPS_N * 32;
+    constexpr int WM = BM / WARPS_M, WN = BN / WARPS_N;
+    constexpr int MT = WM / 8, NTL = WN / 8;
+    constexpr int A_ELEMS = A_KMAJ ? BM * (GEMM_BK + 4) : (BM + 4) * GEMM_BK;
+    constexpr int B_ELEMS = B_KMAJ ? BN * (GEMM_BK + 4) : (BN + 4) * GEMM_BK;
+    extern __shared__ __align__(16) double smem[];
+    double *sA = smem;
+    double *sB = smem + GEMM_STAGES * A_ELEMS;
+
+    const TileRef tr = tiles[blockIdx.x];
+    const GemmTask tk = tasks[tr.task];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = warp % WARPS_M, wn = warp / WARPS_M;
+    const int i0 = tr.ti * BM, j0 = tr.tj * BN;
+    const int rowsA = min(BM, tk.M - i0), rowsB = min(BN, tk.N - j0);
+
+    const double *gA = sp.base[tk.flags & 7] + tk.a + (A_KMAJ ? (long long)i0 * tk.lda : (long long)i0);
+    const double *gB = sp.base[(tk.flags >> 3) & 7] + tk.b + (B_KMAJ ? (long long)j0 * tk.ldb : (long long)j0);
+    const int *gather = (tk.flags & GF_GATHER_A) ? sp.idx + tk.aidx : nullptr;
+
+    double acc[MT][NTL][2];
+#pragma unroll
+    for (int a = 0; a < MT; a++)
+#pragma unroll
+        for (int b = 0; b < NTL; b++) { acc[a][b][0] = 0.0; acc[a][b][1] = 0.0; }
+
+    const int nk = (tk.K + GEMM_BK - 1) / GEMM_BK;
+#pragma unroll
+    for (int s = 0; s < GEMM_STAGES - 1; s++) {
+        if (s < nk) {
+            load_tile<BM, A_KMAJ, NT>(sA + s * A_ELEMS, gA, tk.lda, rowsA, s * GEMM_BK, tk.K, gather, tid);
+            load_tile<BN, B_KMAJ, NT>(sB + s * B_ELEMS, gB, tk.ldb, rowsB, s * GEMM_BK, tk.K, nullptr, tid);
+        }
+        cp_async_commit();
+    }
+    const int lr = lane >> 2, lc = lane & 3;
+    for (int kt = 0; kt < nk; kt++) {
+        cp_async_wait<GEMM_STAGES - 2>();
+        __syncthreads();
+        {   // prefetch stage kt + STAGES-1 into the slot freed by iteration kt-1
+            const int nx = kt + GEMM_STAGES - 1;
+            if (nx < nk) {
+                const int s = nx % GEMM_STAGES;
+                load_tile<BM, A_KMAJ, NT>(sA + s * A_ELEMS, gA, tk.lda, rowsA, nx * GEMM_BK, tk.K, gather, tid);
+                load_tile<BN, B_KMAJ, NT>(sB + s * B_ELEMS, gB, tk.ldb, rowsB, nx * GEMM_BK, tk.K, nullptr, tid);
+            }
+            cp_async_commit();
+        }
+        const double *cA = sA + (kt % GEMM_STAGES) * A_ELEMS;
+        const double *cB = sB + (kt % GEMM_STAGES) * B_ELEMS;
+#pragma unroll
+        for (int k4 = 0; k4 < GEMM_BK; k4 += 4) {
+            double fa[MT], fb[NTL];
+#pragma unroll
+            for (int a = 0; a < MT; a++) {
+                const int i = wm * WM + a * 8 + lr;
+                fa[a] = A_KMAJ ? cA[i * (GEMM_BK + 4) + k4 + lc] : cA[(k4 + lc) * (BM + 4) + i];
+            }
+#pragma unroll
+            for (int b = 0; b < NTL; b++) {
+                const int j = wn * WN + b * 8 + lr;
+                fb[b] = B_KMAJ ? cB[j * (GEMM_BK + 4) + k4 + lc] : cB[(k4 + lc) * (BN + 4) + j];
+            }
+#pragma unroll
+            for (int a = 0; a < MT; a++)
+#pragma unroll
+                for (int b = 0; b < NTL; b++) dmma884(acc[a][b][0], acc[a][b][1], fa[a], fb[b]);
+        }
+    }
+    cp_async_wait<0>();
+
+    // epilogue: each thread owns C[row = lane/4][cols 2*(lane%4), +1] of every 8x8 tile
+    double *gC = sp.base[(tk.flags >> 6) & 7] + tk.c;
+    const int *scat = (tk.flags & GF_SCATTER_C) ? sp.idx + tk.cidx : nullptr;
+    const bool neg = tk.flags & GF_NEG, beta0 = tk.flags & GF_BETA0, lower = tk.flags & GF_LOWER;
+    const bool atomic = tk.flags & GF_ATOMIC, mirror = tk.flags & GF_UPPER_MIRROR;
+#pragma unroll
+    for (int a = 0; a < MT; a++) {
+        const int r = i0 + wm * WM + a * 8 + lr;
+        if (r >= tk.M) continue;
+#pragma unroll
+        for (int b = 0; b < NTL; b++) {
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                const int c = j0 + wn * WN + b * 8 + lc * 2 + e;
+                if (c >= tk.N) continue;
+                if (lower && r < c) continue;
+                const double v = neg ? -acc[a][b][e] : acc[a][b][e];
+                const long long col = scat ? (long long)scat[c] : (long long)c;
+                double *p = gC + r + col * tk.ldc;
+                if (atomic) atomicAdd(p, v);
+                else if (beta0) *p = v;
+                else *p += v;
+                if (mirror) {
+                    double *q = gC - tk.c + tk.c2 + c + (long long)r * tk.ldc;
+                    if (beta0) *q = v; else *q += v;
+                }
+            }
+        }
+    }
+}
+
+}  // namespace spde

@@ -1,0 +1,572 @@
+// plan.cu -- device side of the supernodal multifrontal method: small kernels (scatter, POTRF,
+// extend-add, gathers, reductions), the program executor and the C ABI for plan / factor / solve
+// / selected inverse.
+#include <cmath>
+#include <cstring>
+
+#include "plan.h"
+
+namespace spde {
+
+static thread_local std::string g_err;
+void set_error(const std::string &msg) { g_err = msg; }
+
+// ---------------------------------------------------------------------------------------------
+// K4: Q (slot layout, original ordering) -> zeroed L store (permuted supernodal panels);
+// optional diagonal update tau * cnt  (Q_c = Q + tau S^T S, advection_diffusion2D.py:192)
+__global__ void k_scatter_q(const double *__restrict__ Q, const long long *__restrict__ qdest,
+                            const int *__restrict__ cand, int ncand, int n, int diag_slot,
+                            const double *__restrict__ cnt, double tau, double *__restrict__ L)
+{
+    const long long total = (long long)ncand * n;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const long long d = qdest[e];
+        if (d < 0) continue;
+        const int ci = (int)(e / n), node = (int)(e % n);
+        const int slot = cand[ci];
+        double v = Q[(long long)slot * n + node];
+        if (cnt && slot == diag_slot) v += cnt[node] * tau;
+        L[d] = v;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// extend-add: child update matrix (lower triangle) -> parent panel / parent update matrix
+__global__ void k_extend_add(const ExtTask *__restrict__ tasks, const TileRef *__restrict__ tiles, GemmSpaces sp)
+{
+    const TileRef tr = tiles[blockIdx.x];
+    const ExtTask t = tasks[tr.task];
+    const int *rel = sp.idx + t.rel;
+    const double *src = sp.base[t.src_space] + t.src;
+    double *dst = sp.base[t.dst_space];
+    double *panel = sp.base[0] + t.ppanel;
+    const int i = tr.ti * 32 + threadIdx.x;
+    if (i >= t.nr) return;
+    const int ri = rel[i];
+    for (int jj = threadIdx.y; jj < 32; jj += blockDim.y) {
+        const int j = tr.tj * 32 + jj;
+        if (j >= t.nr || j > i) continue;
+        const double v = src[i + (long long)j * t.lds];
+        const int rj = rel[j];
+        if (rj < t.pnc) {
+            const int row = ri < t.pnc ? ri : t.pncp + (ri - t.pnc);
+            panel[row + (long long)rj * t.pld] += v;
+        } else {
+            dst[t.pupd + (ri - t.pnc) + (long long)(rj - t.pnc) * t.pldu] += v;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// POTRF of one diagonal block (b <= 64) in shared memory + explicit inverse of the factor.
+// One CTA per block; right-looking column sweep, then forward substitution on the identity.
+__global__ void __launch_bounds__(256) k_potrf(const PotrfTask *__restrict__ tasks, double *__restrict__ L,
+                                               double *__restrict__ dinv, int *__restrict__ status)
+{
+    // lower triangle: the block / its factor; strict upper triangle: W^T (W = L^-1); wd: diag(W)
+    __shared__ double a[NB][NB + 1];
+    __shared__ double wd[NB];
+    __shared__ int bad;
+    const PotrfTask t = tasks[blockIdx.x];
+    double *blk = L + t.blk;
+    const int b = t.b, tid = threadIdx.x;
+    if (tid == 0) bad = -1;
+    for (int e = tid; e < NB * NB; e += 256) {
+        const int i = e % NB, j = e / NB;
+        a[i][j] = (i < b && j < b && i >= j) ? blk[i + (long long)j * t.ld] : 0.0;
+    }
+    if (tid < NB) wd[tid] = 0.0;
+    __syncthreads();
+    for (int j = 0; j < b; j++) {
+        if (tid == 0) {
+            const double d = a[j][j];
+            if (!(d > 0.0)) { if (bad < 0) bad = j; a[j][j] = nan(""); }
+            else a[j][j] = sqrt(d);
+        }
+        __syncthreads();
+        const double ljj = a[j][j];
+        for (int i = j + 1 + tid; i < b; i += 256) a[i][j] /= ljj;
+        __syncthreads();
+        // trailing update: (i,c) with j < c <= i < b
+        const int rem = b - j - 1;
+        for (int e = tid; e < rem * rem; e += 256) {
+            const int i = j + 1 + e % rem, c = j + 1 + e / rem;
+            if (c <= i) a[i][c] -= a[i][j] * a[c][j];
+        }
+        __syncthreads();
+    }
+    // W = L^-1 by forward substitution on the identity, one column per thread; column c of W is
+    // kept in row c of the (free) upper triangle, so reads of thread c stay in its own row.
+    if (tid < b) {
+        const int c = tid;
+        const double wcc = 1.0 / a[c][c];
+        wd[c] = wcc;
+        for (int i = c + 1; i < b; i++) {
+            double s = -a[i][c] * wcc;
+            for (int k = c + 1; k < i; k++) s -= a[i][k] * a[c][k];
+            a[c][i] = s / a[i][i];
+        }
+    }
+    __syncthreads();
+    for (int e = tid; e < NB * NB; e += 256) {
+        const int i = e % NB, j = e / NB;
+        if (i < b && j < b) blk[i + (long long)j * t.ld] = (i >= j) ? a[i][j] : 0.0;
+        double wv = 0.0;
+        if (i < b && j < b) wv = (i > j) ? a[j][i] : (i == j ? wd[i] : 0.0);
+        dinv[t.dinv + e] = wv;
+    }
+    if (tid == 0 && bad >= 0) atomicCAS(status, 0, t.col0 + bad + 1);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K6: log-determinant, two deterministic stages (warp shuffles, fixed summation order)
+__global__ void k_logdet_partial(const double *__restrict__ L, const long long *__restrict__ diagpos, int n,
+                                 double *__restrict__ partial)
+{
+    double s = 0.0;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) s += log(L[diagpos[j]]);
+    __shared__ double sh[32];
+    for (int o = 16; o; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        s = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : 0.0;
+        for (int o = 16; o; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+        if (threadIdx.x == 0) partial[blockIdx.x] = s;
+    }
+}
+__global__ void k_sum_final(const double *__restrict__ partial, int m, double scale, double *__restrict__ out)
+{
+    double s = 0.0;
+    for (int j = threadIdx.x; j < m; j += blockDim.x) s += partial[j];
+    __shared__ double sh[32];
+    for (int o = 16; o; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        s = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : 0.0;
+        for (int o = 16; o; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+        if (threadIdx.x == 0) out[0] = s * scale;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// permutations between the caller's row-major n x k block (original ordering) and the solver's
+// k-major, permuted work array Xp[kp x n]
+__global__ void k_perm_in(const double *__restrict__ X, const int *__restrict__ perm, int n, int k, int kp,
+                          int use_perm, double *__restrict__ Xp)
+{
+    const long long total = (long long)n * kp;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const int p = (int)(e % kp), j = (int)(e / kp);
+        const int src = use_perm ? perm[j] : j;
+        Xp[e] = p < k ? X[(long long)src * k + p] : 0.0;
+    }
+}
+__global__ void k_perm_out(const double *__restrict__ Xp, const int *__restrict__ perm, int n, int k, int kp,
+                           int use_perm, double *__restrict__ X)
+{
+    const long long total = (long long)n * k;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const int p = (int)(e % k), j = (int)(e / k);
+        const int dst = use_perm ? perm[j] : j;
+        X[(long long)dst * k + p] = Xp[(long long)j * kp + p];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// selected inverse helpers
+__global__ void k_selinv_gather(const GatherTask *__restrict__ tasks, const TileRef *__restrict__ tiles, GemmSpaces sp)
+{
+    const TileRef tr = tiles[blockIdx.x];
+    const GatherTask t = tasks[tr.task];
+    const int *rel = sp.idx + t.rel;
+    const double *src = sp.base[t.src_space] + t.src;
+    double *dst = sp.base[t.dst_space] + t.dst;
+    const int i = tr.ti * 32 + threadIdx.x;
+    if (i >= t.nr) return;
+    int ri = rel[i];
+    ri = ri < t.pnc ? ri : t.pncp + (ri - t.pnc);
+    for (int jj = threadIdx.y; jj < 32; jj += blockDim.y) {
+        const int j = tr.tj * 32 + jj;
+        if (j >= t.nr) continue;
+        int rj = rel[j];
+        rj = rj < t.pnc ? rj : t.pncp + (rj - t.pnc);
+        dst[(t.ncp + i) + (long long)(t.ncp + j) * t.ldd] = src[ri + (long long)rj * t.lds];
+    }
+}
+__global__ void __launch_bounds__(256) k_wtw(const WtwTask *__restrict__ tasks, const double *__restrict__ dinv, GemmSpaces sp)
+{
+    __shared__ double w[NB][NB + 1];
+    const WtwTask t = tasks[blockIdx.x];
+    for (int e = threadIdx.x; e < NB * NB; e += 256) w[e % NB][e / NB] = dinv[t.w + e];
+    __syncthreads();
+    double *dst = sp.base[t.space] + t.dst;
+    for (int e = threadIdx.x; e < t.b * t.b; e += 256) {
+        const int i = e % t.b, j = e / t.b;
+        double s = 0.0;
+        for (int k = max(i, j); k < t.b; k++) s += w[k][i] * w[k][j];
+        dst[i + (long long)j * t.ldd] = s;
+    }
+}
+__global__ void k_extract(const ZEntry *__restrict__ ent, long long a0, long long a1, const double *__restrict__ zar,
+                          double *__restrict__ Zq)
+{
+    for (long long e = a0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; e < a1; e += (long long)gridDim.x * blockDim.x) {
+        const ZEntry z = ent[e];
+        const double v = zar[z.src];
+        Zq[z.dst] = v;
+        if (z.dst2 >= 0) Zq[z.dst2] = v;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// executor
+
+template <int BM, int BN, int WMn, int WNn, bool AK, bool BK_>
+static cudaError_t launch_gemm_variant(const Launch &L, const Program &P, const GemmSpaces &sp, cudaStream_t st)
+{
+    auto kern = k_gemm_grouped<BM, BN, WMn, WNn, AK, BK_>;
+    constexpr int smem = gemm_smem_bytes<BM, BN>();
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
+    kern<<<L.ntiles, WMn * WNn * 32, smem, st>>>(P.d_gemm + L.task0, P.d_tiles + L.tile0, sp);
+    return cudaGetLastError();
+}
+
+static cudaError_t launch_gemm(const Launch &L, const Program &P, const GemmSpaces &sp, cudaStream_t st)
+{
+    const int cfg = L.variant / 4, ak = (L.variant >> 1) & 1, bk = L.variant & 1;
+#define V(c, A, B)                                                                                     \
+    if (cfg == c && ak == A && bk == B) {                                                              \
+        if (c == 0) return launch_gemm_variant<128, 128, 2, 4, A, B>(L, P, sp, st);                     \
+        if (c == 1) return launch_gemm_variant<128, 64, 4, 2, A, B>(L, P, sp, st);                      \
+        return launch_gemm_variant<64, 64, 2, 2, A, B>(L, P, sp, st);                                   \
+    }
+    V(0, false, false) V(0, false, true) V(0, true, false) V(0, true, true)
+    V(1, false, false) V(1, false, true) V(1, true, false) V(1, true, true)
+    V(2, false, false) V(2, false, true) V(2, true, false) V(2, true, true)
+#undef V
+    return cudaErrorInvalidValue;
+}
+
+template <class T>
+static cudaError_t upload(const std::vector<T> &h, T **d)
+{
+    if (h.empty()) { *d = nullptr; return cudaSuccess; }
+    cudaError_t e = cudaMalloc((void **)d, h.size() * sizeof(T));
+    if (e != cudaSuccess) return e;
+    return cudaMemcpy(*d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice);
+}
+
+static int upload_program(Program &P)
+{
+    if (P.uploaded) return SPDE_OK;
+    SPDE_CUDA_CHECK(upload(P.gemm, &P.d_gemm));
+    SPDE_CUDA_CHECK(upload(P.tiles, &P.d_tiles));
+    SPDE_CUDA_CHECK(upload(P.potrf, &P.d_potrf));
+    SPDE_CUDA_CHECK(upload(P.ext, &P.d_ext));
+    SPDE_CUDA_CHECK(upload(P.gather, &P.d_gather));
+    SPDE_CUDA_CHECK(upload(P.wtw, &P.d_wtw));
+    P.uploaded = true;
+    return SPDE_OK;
+}
+
+static void free_program(Program &P)
+{
+    cudaFree(P.d_gemm); cudaFree(P.d_tiles); cudaFree(P.d_potrf); cudaFree(P.d_ext); cudaFree(P.d_gather); cudaFree(P.d_wtw);
+    P.uploaded = false;
+}
+
+static GemmSpaces spaces_of(Plan &p, int which)
+{
+    GemmSpaces sp;
+    sp.base[0] = p.d_L[which];
+    sp.base[1] = p.d_arena[0];
+    sp.base[2] = p.d_arena[1];
+    sp.base[3] = p.d_dinv[which];
+    sp.base[4] = p.d_X;
+    sp.base[5] = p.d_ybuf;
+    sp.base[6] = p.d_zarena[0];
+    sp.base[7] = p.d_zarena[1];
+    sp.idx = p.d_idx;
+    return sp;
+}
+
+static int run_program(Plan &p, Program &P, int which, cudaStream_t st, double *d_Zq)
+{
+    int rc = upload_program(P);
+    if (rc) return rc;
+    GemmSpaces sp = spaces_of(p, which);
+    for (const Launch &L : P.launches) {
+        switch (L.kind) {
+        case LK_GEMM:
+            SPDE_CUDA_CHECK(launch_gemm(L, P, sp, st));
+            break;
+        case LK_POTRF:
+            k_potrf<<<L.ntasks, 256, 0, st>>>(P.d_potrf + L.task0, p.d_L[which], p.d_dinv[which], p.d_status);
+            break;
+        case LK_EXTADD:
+            k_extend_add<<<L.ntiles, dim3(32, 8), 0, st>>>(P.d_ext + L.task0, P.d_tiles + L.tile0, sp);
+            break;
+        case LK_ZERO:
+            SPDE_CUDA_CHECK(cudaMemsetAsync(sp.base[L.variant] + L.a0, 0, (size_t)(L.a1 - L.a0) * sizeof(double), st));
+            break;
+        case LK_GATHER:
+            k_selinv_gather<<<L.ntiles, dim3(32, 8), 0, st>>>(P.d_gather + L.task0, P.d_tiles + L.tile0, sp);
+            break;
+        case LK_WTW:
+            k_wtw<<<L.ntasks, 256, 0, st>>>(P.d_wtw + L.task0, p.d_dinv[which], sp);
+            break;
+        case LK_EXTRACT: {
+            const long long cnt = L.a1 - L.a0;
+            k_extract<<<(int)std::min<long long>((cnt + 255) / 256, 148 * 16), 256, 0, st>>>(p.d_zentries, L.a0, L.a1, sp.base[L.variant], d_Zq);
+            break;
+        }
+        }
+        SPDE_LAUNCH_CHECK();
+    }
+    return SPDE_OK;
+}
+
+static int ensure_device(Plan &p, int which)
+{
+    if (!(p.device_ready & 1)) {
+        std::vector<int> idx(p.sym.rows);
+        idx.insert(idx.end(), p.sym.relidx.begin(), p.sym.relidx.end());
+        SPDE_CUDA_CHECK(upload(idx, &p.d_idx));
+        SPDE_CUDA_CHECK(upload(p.qdest, &p.d_qdest));
+        SPDE_CUDA_CHECK(upload(p.diagpos, &p.d_diagpos));
+        SPDE_CUDA_CHECK(upload(p.cand_slots, &p.d_cand));
+        SPDE_CUDA_CHECK(upload(p.sym.perm, &p.d_perm));
+        SPDE_CUDA_CHECK(cudaMalloc((void **)&p.d_status, sizeof(int)));
+        SPDE_CUDA_CHECK(cudaMalloc((void **)&p.d_red, 4096 * sizeof(double)));
+        for (int a = 0; a < 2; a++)
+            if (p.arena_size[a]) SPDE_CUDA_CHECK(cudaMalloc((void **)&p.d_arena[a], p.arena_size[a] * sizeof(double)));
+        p.device_ready |= 1;
+    }
+    if (!p.d_L[which]) {
+        SPDE_CUDA_CHECK(cudaMalloc((void **)&p.d_L[which], std::max<int64_t>(p.l_size, 2) * sizeof(double)));
+        SPDE_CUDA_CHECK(cudaMalloc((void **)&p.d_dinv[which], std::max<int64_t>(p.dinv_size, 2) * sizeof(double)));
+    }
+    return SPDE_OK;
+}
+
+}  // namespace spde
+
+using namespace spde;
+
+extern "C" int spde_abi_version(void) { return 1; }
+extern "C" const char *spde_last_error(void) { return g_err.c_str(); }
+
+extern "C" int spde_plan_create(int M, int N, int T, int bc, int max_rhs, spde_plan **out)
+{
+    if (M < 2 || N < 2 || T < 1 || bc < 1 || bc > 3 || !out) { set_error("spde_plan_create: bad arguments"); return SPDE_ERR_ARG; }
+    if (bc == 2 && (M < 5 || N < 5)) { set_error("periodic meshes need M,N >= 5"); return SPDE_ERR_ARG; }
+    Plan *p = new Plan();
+    p->max_rhs = max_rhs;
+    p->sym.analyse(Geo{M, N, T, bc});
+    p->rel_base = (int64_t)p->sym.rows.size();
+    p->build_layout();
+    p->build_factor_program();
+    *out = reinterpret_cast<spde_plan *>(p);
+    return SPDE_OK;
+}
+
+extern "C" void spde_plan_destroy(spde_plan *pp)
+{
+    if (!pp) return;
+    Plan *p = reinterpret_cast<Plan *>(pp);
+    for (int a = 0; a < 2; a++) { cudaFree(p->d_L[a]); cudaFree(p->d_dinv[a]); cudaFree(p->d_arena[a]); cudaFree(p->d_zarena[a]); }
+    cudaFree(p->d_ybuf); cudaFree(p->d_X); cudaFree(p->d_red); cudaFree(p->d_idx); cudaFree(p->d_qdest);
+    cudaFree(p->d_diagpos); cudaFree(p->d_cand); cudaFree(p->d_perm); cudaFree(p->d_status); cudaFree(p->d_zentries);
+    free_program(p->factor);
+    free_program(p->selinv);
+    for (auto &kv : p->solve) free_program(kv.second);
+    delete p;
+}
+
+extern "C" int64_t spde_plan_info(const spde_plan *pp, int what)
+{
+    const Plan *p = reinterpret_cast<const Plan *>(pp);
+    switch (what) {
+    case 0: return p->sym.n;
+    case 1: return p->sym.nsuper;
+    case 2: return p->sym.nnzL;
+    case 4: return p->l_size * 8;
+    case 5: return (p->arena_size[0] + p->arena_size[1]) * 8;
+    case 6: return p->sym.maxdepth + 1;
+    case 7: { int m = 0; for (auto &s : p->sn) m = std::max(m, s.nc + s.nr); return m; }
+    case 8: return (int64_t)p->factor.launches.size();
+    case 9: return (int64_t)p->sym.rows.size();
+    case 10: return (p->zarena_size[0] + p->zarena_size[1]) * 8;
+    case 11: return (int64_t)p->factor.gemm.size();
+    case 12: return (int64_t)p->factor.tiles.size();
+    case 13: { int m = 0; for (auto &s : p->sn) m = std::max(m, s.nc); return m; }
+    }
+    return -1;
+}
+extern "C" double spde_plan_info_d(const spde_plan *pp, int what)
+{
+    const Plan *p = reinterpret_cast<const Plan *>(pp);
+    if (what == 3) return p->sym.flops;
+    if (what == 14) return p->factor.flops;   // flops actually scheduled (relaxed supernodes, full blocks)
+    return (double)spde_plan_info(pp, what);
+}
+extern "C" int spde_plan_perm(const spde_plan *pp, int32_t *h_perm)
+{
+    const Plan *p = reinterpret_cast<const Plan *>(pp);
+    memcpy(h_perm, p->sym.perm.data(), sizeof(int) * p->sym.n);
+    return SPDE_OK;
+}
+extern "C" int spde_plan_supernodes(const spde_plan *pp, int32_t *h_first, int64_t *h_rowptr, int32_t *h_rows, int32_t *h_parent)
+{
+    const Plan *p = reinterpret_cast<const Plan *>(pp);
+    const Symbolic &S = p->sym;
+    memcpy(h_first, S.first.data(), sizeof(int) * (S.nsuper + 1));
+    memcpy(h_rowptr, S.rowptr.data(), sizeof(int64_t) * (S.nsuper + 1));
+    memcpy(h_rows, S.rows.data(), sizeof(int) * S.rows.size());
+    memcpy(h_parent, S.sparent.data(), sizeof(int) * S.nsuper);
+    return SPDE_OK;
+}
+
+// Host-side export of the schedules and the storage layout: used by the tests and by the NumPy
+// interpreter in oracle/plan_emulator.py to validate the plan without a GPU.
+extern "C" int spde_plan_export(spde_plan *pp, int prog, int k, int what, void *h_out, int64_t *count, int *elem_size)
+{
+    Plan &p = *reinterpret_cast<Plan *>(pp);
+    Program *P = nullptr;
+    if (prog == 0) P = &p.factor;
+    else if (prog == 1) P = &p.solve_program(k, 0);
+    else if (prog == 2) P = &p.solve_program(k, 1);
+    else if (prog == 3) { p.build_selinv_program(); P = &p.selinv; }
+    const void *src = nullptr;
+    int64_t cnt = 0;
+    int es = 0;
+#define EXP(vec) { src = (vec).data(); cnt = (int64_t)(vec).size(); es = (int)sizeof((vec)[0]); }
+    if (prog >= 0 && prog <= 3) {
+        switch (what) {
+        case 0: EXP(P->launches) break;
+        case 1: EXP(P->gemm) break;
+        case 2: EXP(P->tiles) break;
+        case 3: EXP(P->potrf) break;
+        case 4: EXP(P->ext) break;
+        case 5: EXP(P->gather) break;
+        case 6: EXP(P->wtw) break;
+        default: set_error("spde_plan_export: bad what"); return SPDE_ERR_ARG;
+        }
+    } else if (prog == 4) {   // layout
+        static std::vector<int64_t> sizes;
+        static std::vector<int> idx;
+        switch (what) {
+        case 0: sizes = {p.l_size, p.dinv_size, p.arena_size[0], p.arena_size[1], p.zarena_size[0], p.zarena_size[1], p.ybuf_size, p.rel_base};
+                EXP(sizes) break;
+        case 1: EXP(p.qdest) break;
+        case 2: EXP(p.cand_slots) break;
+        case 3: EXP(p.diagpos) break;
+        case 4: idx = p.sym.rows; idx.insert(idx.end(), p.sym.relidx.begin(), p.sym.relidx.end()); EXP(idx) break;
+        case 5: EXP(p.zentries) break;
+        case 6: EXP(p.zdepth_ptr) break;
+        case 7: EXP(p.sym.colcount) break;
+        default: set_error("spde_plan_export: bad what"); return SPDE_ERR_ARG;
+        }
+    } else { set_error("spde_plan_export: bad prog"); return SPDE_ERR_ARG; }
+#undef EXP
+    if (count) *count = cnt;
+    if (elem_size) *elem_size = es;
+    if (h_out && cnt) memcpy(h_out, src, (size_t)cnt * es);
+    return SPDE_OK;
+}
+
+extern "C" int spde_factorize(spde_plan *pp, int which, const double *d_Q, const double *d_cnt, double tau, void *stream)
+{
+    Plan &p = *reinterpret_cast<Plan *>(pp);
+    if (which < 0 || which > 1) { set_error("spde_factorize: which must be 0 or 1"); return SPDE_ERR_ARG; }
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = ensure_device(p, which);
+    if (rc) return rc;
+    const int n = p.sym.n;
+    SPDE_CUDA_CHECK(cudaMemsetAsync(p.d_L[which], 0, (size_t)p.l_size * sizeof(double), st));
+    SPDE_CUDA_CHECK(cudaMemsetAsync(p.d_status, 0, sizeof(int), st));
+    const int ncand = (int)p.cand_slots.size();
+    k_scatter_q<<<148 * 8, 256, 0, st>>>(d_Q, p.d_qdest, p.d_cand, ncand, n, p.sym.nslots / 2, d_cnt, tau, p.d_L[which]);
+    SPDE_LAUNCH_CHECK();
+    rc = run_program(p, p.factor, which, st, nullptr);
+    if (rc) return rc;
+    int h = 0;
+    SPDE_CUDA_CHECK(cudaMemcpyAsync(&h, p.d_status, sizeof(int), cudaMemcpyDeviceToHost, st));
+    SPDE_CUDA_CHECK(cudaStreamSynchronize(st));
+    p.factored[which] = true;
+    p.status[which] = h ? SPDE_ERR_NOT_SPD : SPDE_OK;
+    p.bad_col[which] = h - 1;
+    if (h) { set_error("matrix is not positive definite (pivot " + std::to_string(h - 1) + " of the permuted matrix)"); return SPDE_ERR_NOT_SPD; }
+    return SPDE_OK;
+}
+
+extern "C" int spde_factor_info(spde_plan *pp, int which, int *h_status, int *h_bad_column)
+{
+    Plan &p = *reinterpret_cast<Plan *>(pp);
+    if (h_status) *h_status = p.status[which];
+    if (h_bad_column) *h_bad_column = p.bad_col[which];
+    return SPDE_OK;
+}
+
+extern "C" int spde_logdet(spde_plan *pp, int which, double *h_logdet, void *stream)
+{
+    Plan &p = *reinterpret_cast<Plan *>(pp);
+    if (!p.factored[which]) { set_error("spde_logdet: not factorised"); return SPDE_ERR_ARG; }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nb = 1024;
+    k_logdet_partial<<<nb, 256, 0, st>>>(p.d_L[which], p.d_diagpos, p.sym.n, p.d_red);
+    k_sum_final<<<1, 1024, 0, st>>>(p.d_red, nb, 2.0, p.d_red + nb);
+    SPDE_LAUNCH_CHECK();
+    SPDE_CUDA_CHECK(cudaMemcpyAsync(h_logdet, p.d_red + nb, sizeof(double), cudaMemcpyDeviceToHost, st));
+    SPDE_CUDA_CHECK(cudaStreamSynchronize(st));
+    return SPDE_OK;
+}
+
+extern "C" int spde_solve(spde_plan *pp, int which, int mode, double *d_X, int k, void *stream)
+{
+    Plan &p = *reinterpret_cast<Plan *>(pp);
+    if (!p.factored[which] || k < 1 || mode < 0 || mode > 2) { set_error("spde_solve: bad state/arguments"); return SPDE_ERR_ARG; }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int n = p.sym.n, kp = k + (k & 1);
+    const int64_t need = (int64_t)n * kp;
+    if (p.x_cap < need) {
+        cudaFree(p.d_X);
+        p.d_X = nullptr;
+        p.x_cap = 0;
+        SPDE_CUDA_CHECK(cudaMalloc((void **)&p.d_X, need * sizeof(double)));
+        p.x_cap = need;
+    }
+    const int grid = 148 * 8;
+    k_perm_in<<<grid, 256, 0, st>>>(d_X, p.d_perm, n, k, kp, mode != 1, p.d_X);
+    SPDE_LAUNCH_CHECK();
+    int rc;
+    if (mode == 0 || mode == 2) { rc = run_program(p, p.solve_program(k, 0), which, st, nullptr); if (rc) return rc; }
+    if (mode == 0 || mode == 1) { rc = run_program(p, p.solve_program(k, 1), which, st, nullptr); if (rc) return rc; }
+    k_perm_out<<<grid, 256, 0, st>>>(p.d_X, p.d_perm, n, k, kp, mode != 2, d_X);
+    SPDE_LAUNCH_CHECK();
+    return SPDE_OK;
+}
+
+extern "C" int spde_selinv(spde_plan *pp, int which, double *d_Zq, void *stream)
+{
+    Plan &p = *reinterpret_cast<Plan *>(pp);
+    if (!p.factored[which]) { set_error("spde_selinv: not factorised"); return SPDE_ERR_ARG; }
+    cudaStream_t st = (cudaStream_t)stream;
+    p.build_selinv_program();
+    if (!(p.device_ready & 2)) {
+        for (int a = 0; a < 2; a++)
+            if (p.zarena_size[a]) SPDE_CUDA_CHECK(cudaMalloc((void **)&p.d_zarena[a], p.zarena_size[a] * sizeof(double)));
+        SPDE_CUDA_CHECK(cudaMalloc((void **)&p.d_ybuf, std::max<int64_t>(p.ybuf_size, 2) * sizeof(double)));
+        SPDE_CUDA_CHECK(upload(p.zentries, &p.d_zentries));
+        p.device_ready |= 2;
+    }
+    SPDE_CUDA_CHECK(cudaMemsetAsync(d_Zq, 0, (size_t)p.sym.nslots * p.sym.n * sizeof(double), st));
+    return run_program(p, p.selinv, which, st, d_Zq);
+}

@@ -1,0 +1,106 @@
+// plan.h -- numeric plan of the supernodal multifrontal method: storage layout, per-level kernel
+// task lists ("programs") for factorisation, triangular solves and the selected inverse.
+// Built on the host once per mesh from the Symbolic analysis; executed by plan.cu.
+#pragma once
+#include <map>
+#include <vector>
+
+#include "gemm.cuh"
+#include "symbolic.h"
+
+namespace spde {
+
+constexpr int NB = 64;        // diagonal-block size of the dense partial Cholesky
+constexpr int OUTER = 4;      // inner blocks per outer (right-looking) block -> 256 columns
+
+struct SNode {
+    int first, nc, nr, ncp, ld, nblk, depth, parent, ldu;
+    int64_t panel;     // offset of the m x nc panel in the L store (ld = ncp + roundup2(nr))
+    int64_t dinv;      // offset of the nblk 64x64 inverse diagonal blocks
+    int64_t upd;       // offset of the nr x nr update matrix inside arena[depth & 1]
+    int64_t front;     // offset of the ld x ld selected-inverse front inside zarena[depth & 1]
+    int64_t rows;      // offset into the device index array of the structure rows
+};
+
+struct PotrfTask { long long blk; long long dinv; int ld, b, col0, pad; };
+// extend-add of one child update matrix into its parent's front
+struct ExtTask {
+    long long src; int lds, nr;            // child update matrix (arena of the child's parity)
+    long long ppanel; int pld, pnc, pncp;  // parent panel
+    long long pupd; int pldu;              // parent update matrix
+    int rel;                               // offset of the child's relative indices
+    int src_space, dst_space;
+};
+struct GatherTask {   // selected inverse: child's trailing block <- parent's front
+    long long dst; int ldd, ncp, nr;       // child front (zarena of child's parity), trailing block at (ncp,ncp)
+    long long src; int lds, pnc, pncp;     // parent front
+    int rel;
+    int src_space, dst_space;
+};
+struct WtwTask { long long w; long long dst; int ldd, b, space, pad; };
+
+enum LaunchKind : int { LK_GEMM = 0, LK_POTRF, LK_EXTADD, LK_ZERO, LK_GATHER, LK_WTW, LK_EXTRACT };
+
+struct Launch {
+    int kind, variant;
+    int64_t task0; int ntasks;
+    int64_t tile0; int ntiles;
+    int64_t a0, a1;   // LK_ZERO: [a0,a1) doubles of space `variant`; LK_EXTRACT: entry range
+};
+
+struct Program {
+    std::vector<Launch> launches;
+    std::vector<GemmTask> gemm;
+    std::vector<TileRef> tiles;
+    std::vector<PotrfTask> potrf;
+    std::vector<ExtTask> ext;
+    std::vector<GatherTask> gather;
+    std::vector<WtwTask> wtw;
+    // device copies
+    GemmTask *d_gemm = nullptr; TileRef *d_tiles = nullptr; PotrfTask *d_potrf = nullptr;
+    ExtTask *d_ext = nullptr; GatherTask *d_gather = nullptr; WtwTask *d_wtw = nullptr;
+    bool uploaded = false;
+    double flops = 0;
+};
+
+struct ZEntry { long long dst, dst2; long long src; int sn, pad; };   // selected-inverse extraction
+
+struct Plan {
+    Symbolic sym;
+    std::vector<SNode> sn;
+    std::vector<std::vector<int>> by_depth;
+    int64_t l_size = 0, dinv_size = 0, arena_size[2] = {0, 0}, zarena_size[2] = {0, 0}, ybuf_size = 0;
+    int max_rhs = 0;
+    // scatter map Q slots -> L store
+    std::vector<int> cand_slots;           // slots that can hold a lower-triangle entry
+    std::vector<long long> qdest;          // cand x n, -1 = unused
+    std::vector<long long> diagpos;        // n, position of L(j,j) in the L store (new order)
+    std::vector<ZEntry> zentries;          // grouped by depth
+    std::vector<int64_t> zdepth_ptr;
+    Program factor;
+    std::map<std::pair<int, int>, Program> solve;   // (k, direction) -> program
+    Program selinv;
+    bool selinv_built = false;
+    // device state
+    int device_ready = 0;
+    double *d_L[2] = {nullptr, nullptr};
+    double *d_dinv[2] = {nullptr, nullptr};
+    double *d_arena[2] = {nullptr, nullptr};
+    double *d_zarena[2] = {nullptr, nullptr};
+    double *d_ybuf = nullptr, *d_X = nullptr, *d_red = nullptr;
+    int64_t x_cap = 0;
+    int *d_idx = nullptr;          // rows | relidx
+    int64_t rel_base = 0;
+    long long *d_qdest = nullptr, *d_diagpos = nullptr;
+    int *d_cand = nullptr, *d_perm = nullptr, *d_status = nullptr;
+    ZEntry *d_zentries = nullptr;
+    int status[2] = {0, 0}, bad_col[2] = {-1, -1};
+    bool factored[2] = {false, false};
+
+    void build_layout();
+    void build_factor_program();
+    Program &solve_program(int k, int dir);
+    void build_selinv_program();
+};
+
+}  // namespace spde

@@ -1,0 +1,282 @@
+// reduce.cu -- K8/K9/K11: likelihood reductions and the gradient contraction.
+//
+//   spde_q_apply           y = Q x on the slot layout (stencil apply; no index arrays)
+//   spde_dot               deterministic two-stage sum(x .* y), warp shuffles
+//   spde_sddmm             W[slot,node] = alpha * <X[node,:], Y[nbr(node,slot),:]> on the pattern of Q
+//                          (turns the Hutchinson traces of advection_diffusion2D.py:204-206 into
+//                          weights on the pattern; the same weights come from the Takahashi inverse)
+//   spde_assembly_adjoint  d sum(W .* Q) / d A9, d Qs, d Q0 -- the transpose of K3, so that
+//                          sum(W .* dQ_i) for *every* parameter i costs one pass instead of one
+//                          sparse n x n matrix per parameter (advection_diffusion2D.py:119-182)
+//   spde_gemv_t            out = B^T u for the spline-basis chain rule
+// All are HBM-bound streaming kernels.
+#include "common.cuh"
+
+namespace spde {
+
+__device__ __forceinline__ double warp_sum(double s)
+{
+    for (int o = 16; o; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    return s;
+}
+
+__device__ __forceinline__ double block_sum(double s, double *sh)
+{
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        s = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : 0.0;
+        s = warp_sum(s);
+    }
+    return s;   // valid in thread 0
+}
+
+__global__ void k_q_apply(Geo g, const double *__restrict__ Q, const double *__restrict__ X, int k,
+                          double *__restrict__ Y)
+{
+    const long long n = (long long)g.M * g.N * g.T;
+    const long long total = n * k;
+    const int ns = g.nslots();
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const int node = (int)(e / k), p = (int)(e % k);
+        double s = 0.0;
+        for (int q = 0; q < ns; q++) {
+            const int c = g.slot_nbr(node, q);
+            if (c < 0) continue;
+            s += Q[(long long)q * n + node] * X[(long long)c * k + p];
+        }
+        Y[e] = s;
+    }
+}
+
+__global__ void k_dot_partial(const double *__restrict__ X, const double *__restrict__ Y, long long len,
+                              double *__restrict__ partial)
+{
+    __shared__ double sh[32];
+    double s = 0.0;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < len; e += (long long)gridDim.x * blockDim.x)
+        s += X[e] * Y[e];
+    s = block_sum(s, sh);
+    if (threadIdx.x == 0) partial[blockIdx.x] = s;
+}
+__global__ void k_final(const double *__restrict__ partial, int m, double *__restrict__ out)
+{
+    __shared__ double sh[32];
+    double s = 0.0;
+    for (int j = threadIdx.x; j < m; j += blockDim.x) s += partial[j];
+    s = block_sum(s, sh);
+    if (threadIdx.x == 0) out[0] = s;
+}
+
+// one warp per node: lanes stride over the k probe columns, one shuffle reduction per slot
+__global__ void k_sddmm(Geo g, const double *__restrict__ X, const double *__restrict__ Y, int k, double alpha,
+                        int accumulate, double *__restrict__ W)
+{
+    const long long n = (long long)g.M * g.N * g.T;
+    const int ns = g.nslots();
+    const int lane = threadIdx.x & 31;
+    const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long node = warp0; node < n; node += nwarps) {
+        for (int q = 0; q < ns; q++) {
+            const int c = g.slot_nbr((int)node, q);
+            if (c < 0) continue;
+            double s = 0.0;
+            for (int p = lane; p < k; p += 32) s += X[node * k + p] * Y[(long long)c * k + p];
+            s = warp_sum(s);
+            if (lane == 0) {
+                const long long o = (long long)q * n + node;
+                W[o] = accumulate ? W[o] + alpha * s : alpha * s;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// adjoint of the assembly.  Phase 1 (space-time only): sums of W over the time blocks.
+//   Wd[q][k] = sum_{t>=1} W[9+q][(k,t)]      weights of A^T d A
+//   Wu[s][k] = sum_{t<=T-2} W[34+s][(k,t)]   weights of -(Qs iV) A
+//   Wl[s][k] = sum_{t>=1} W[s][(k,t)]        weights of -A^T iV Qs  (row k, column k+off(s) at t-1)
+//   wq[k]    = sum_{t<=T-2} W[21][(k,t)]     weights of the "+Qs" diagonal
+__global__ void k_adj_time_reduce(Geo g, const double *__restrict__ W, double *__restrict__ Wd, double *__restrict__ Wu,
+                                  double *__restrict__ Wl, double *__restrict__ wq, double *__restrict__ GQ0, double q0scale)
+{
+    const int Ns = g.M * g.N;
+    const long long n = (long long)Ns * g.T;
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const int q = blockIdx.y;   // 0..42
+    if (k >= Ns) return;
+    double s = 0.0;
+    if (q < 9) {
+        for (int t = 1; t < g.T; t++) s += W[(long long)q * n + (long long)t * Ns + k];
+        Wl[(long long)q * Ns + k] = s;
+    } else if (q < 34) {
+        for (int t = 1; t < g.T; t++) s += W[(long long)q * n + (long long)t * Ns + k];
+        Wd[(long long)(q - 9) * Ns + k] = s;
+        GQ0[(long long)(q - 9) * Ns + k] = q0scale * W[(long long)q * n + k];
+        if (q == 21) {
+            double u = 0.0;
+            for (int t = 0; t < g.T - 1; t++) u += W[(long long)q * n + (long long)t * Ns + k];
+            wq[k] = u;
+        }
+    } else {
+        for (int t = 0; t < g.T - 1; t++) s += W[(long long)q * n + (long long)t * Ns + k];
+        Wu[(long long)(q - 34) * Ns + k] = s;
+    }
+}
+
+__device__ __forceinline__ double qs_val(double V, double kap) { const double As = V * kap; return (As * (1.0 / V)) * As; }
+
+// Phase 2: per cell c.  With k_s = c + off(s):
+//   GA[c,s]  = cs*( d_c * sum_s'' A[c,s''] (Wd[k_s -> k_s''] + Wd[k_s'' -> k_s])
+//                   - Qs_c iV (Wu[s][c] + Wl[8-s][k_s]) )
+//   Gq[c]    = cs*( iV^2 sum_{s,s''} A[c,s] A[c,s''] Wd[k_s -> k_s''] + wq[c]
+//                   - iV sum_s A[c,s] (Wu[s][c] + Wl[8-s][k_s]) )          (d S / d Qs_c)
+// Spatial (timed=0): Wd = W, d = iV, cs = 1, no Wu/Wl/wq terms.
+__global__ void k_adj_cell(Geo g, int timed, const double *__restrict__ Wd, const double *__restrict__ Wu,
+                           const double *__restrict__ Wl, const double *__restrict__ wq, const double *__restrict__ A,
+                           const double *__restrict__ kappa, int kvar, double V, double cs,
+                           double *__restrict__ GA, double *__restrict__ Gq)
+{
+    const int Ns = g.M * g.N;
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= Ns) return;
+    const int i = c % g.M, j = c / g.M;
+    const double iV = 1.0 / V;
+    const double qs = timed ? qs_val(V, kvar ? kappa[c] : kappa[0]) : 0.0;
+    const double d = timed ? qs * iV * iV : iV;
+    int nb[9];
+    double a[9];
+#pragma unroll
+    for (int s = 0; s < 9; s++) {
+        nb[s] = g.nbr(i, j, s % 3 - 1, s / 3 - 1);
+        a[s] = A[(long long)s * Ns + c];
+    }
+    double gq = 0.0;
+    for (int s = 0; s < 9; s++) {
+        double ga = 0.0;
+        if (nb[s] >= 0) {
+            const int si = s % 3 - 1, sj = s / 3 - 1;
+            double acc = 0.0;
+            for (int s2 = 0; s2 < 9; s2++) {
+                if (nb[s2] < 0) continue;
+                const int di = (s2 % 3 - 1) - si, dj = (s2 / 3 - 1) - sj;   // k_s -> k_s2
+                const double w1 = Wd[(long long)((dj + 2) * 5 + (di + 2)) * Ns + nb[s]];
+                const double w2 = Wd[(long long)((2 - dj) * 5 + (2 - di)) * Ns + nb[s2]];
+                acc += a[s2] * (w1 + w2);
+                gq += a[s] * a[s2] * w1;
+            }
+            ga = d * acc;
+            if (timed) {
+                const double wul = Wu[(long long)s * Ns + c] + Wl[(long long)(8 - s) * Ns + nb[s]];
+                ga -= qs * iV * wul;
+                gq -= V * a[s] * wul;   // scaled by iV^2 below
+            }
+        }
+        GA[(long long)s * Ns + c] = cs * ga;
+    }
+    if (Gq) Gq[c] = timed ? cs * (iV * iV * gq + wq[c]) : 0.0;
+}
+
+__global__ void k_gemv_t(const double *__restrict__ B, const double *__restrict__ u, int rows, int cols,
+                         double *__restrict__ partial)
+{
+    // one block column-slice: blockIdx.y = column, blocks over rows; partial[col*gridDim.x + blockIdx.x]
+    __shared__ double sh[32];
+    const int col = blockIdx.y;
+    double s = 0.0;
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += gridDim.x * blockDim.x)
+        s += B[(long long)r * cols + col] * u[r];
+    s = block_sum(s, sh);
+    if (threadIdx.x == 0) partial[(long long)col * gridDim.x + blockIdx.x] = s;
+}
+__global__ void k_gemv_final(const double *__restrict__ partial, int nb, double *__restrict__ out)
+{
+    __shared__ double sh[32];
+    double s = 0.0;
+    for (int j = threadIdx.x; j < nb; j += blockDim.x) s += partial[(long long)blockIdx.x * nb + j];
+    s = block_sum(s, sh);
+    if (threadIdx.x == 0) out[blockIdx.x] = s;
+}
+
+static double *g_scratch = nullptr;   // 64 KiB of device scratch for the reductions
+static int ensure_scratch()
+{
+    if (!g_scratch) SPDE_CUDA_CHECK(cudaMalloc((void **)&g_scratch, 8192 * sizeof(double)));
+    return SPDE_OK;
+}
+
+}  // namespace spde
+
+using namespace spde;
+
+extern "C" int spde_q_apply(int M, int N, int T, int bc, const double *d_Q, const double *d_X, int k, double *d_Y, void *stream)
+{
+    Geo g{M, N, T, bc};
+    const long long total = (long long)M * N * T * k;
+    k_q_apply<<<(int)std::min<long long>((total + 255) / 256, 148 * 32), 256, 0, (cudaStream_t)stream>>>(g, d_Q, d_X, k, d_Y);
+    SPDE_LAUNCH_CHECK();
+    return SPDE_OK;
+}
+
+extern "C" int spde_dot(const double *d_X, const double *d_Y, int64_t len, double *h_out, void *stream)
+{
+    int rc = ensure_scratch();
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nb = 1184;   // 8 x 148
+    k_dot_partial<<<nb, 256, 0, st>>>(d_X, d_Y, len, g_scratch);
+    k_final<<<1, 1024, 0, st>>>(g_scratch, nb, g_scratch + nb);
+    SPDE_LAUNCH_CHECK();
+    SPDE_CUDA_CHECK(cudaMemcpyAsync(h_out, g_scratch + nb, sizeof(double), cudaMemcpyDeviceToHost, st));
+    SPDE_CUDA_CHECK(cudaStreamSynchronize(st));
+    return SPDE_OK;
+}
+
+extern "C" int spde_sddmm(int M, int N, int T, int bc, const double *d_X, const double *d_Y, int k, double alpha,
+                          int accumulate, double *d_W, void *stream)
+{
+    Geo g{M, N, T, bc};
+    const long long n = (long long)M * N * T;
+    const long long blocks = std::min<long long>((n * 32 + 255) / 256, 148 * 16);
+    k_sddmm<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(g, d_X, d_Y, k, alpha, accumulate, d_W);
+    SPDE_LAUNCH_CHECK();
+    return SPDE_OK;
+}
+
+extern "C" int spde_assembly_adjoint(int M, int N, int T, int bc, const double *d_W, const double *d_A9,
+                                     const double *d_kappa, int kvar, double V, double sigma, double dt, int timed,
+                                     double *d_work /* 44*Ns doubles */, double *d_GA9, double *d_Gq, double *d_GQ0_25,
+                                     void *stream)
+{
+    Geo g{M, N, T, bc};
+    const int Ns = M * N;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (timed) {
+        if (!d_work || !d_GQ0_25 || !d_Gq) { set_error("spde_assembly_adjoint: work buffers required"); return SPDE_ERR_ARG; }
+        double *Wd = d_work, *Wu = Wd + (size_t)25 * Ns, *Wl = Wu + (size_t)9 * Ns, *wq = Wl + (size_t)9 * Ns;
+        const double cs = 1 / (dt * sigma);
+        k_adj_time_reduce<<<dim3(cdiv(Ns, 128), 43), 128, 0, st>>>(g, d_W, Wd, Wu, Wl, wq, d_GQ0_25, cs * (sigma * dt));
+        SPDE_LAUNCH_CHECK();
+        Geo g2{M, N, 1, bc};
+        k_adj_cell<<<cdiv(Ns, 128), 128, 0, st>>>(g2, 1, Wd, Wu, Wl, wq, d_A9, d_kappa, kvar, V, cs, d_GA9, d_Gq);
+    } else {
+        k_adj_cell<<<cdiv(Ns, 128), 128, 0, st>>>(g, 0, d_W, nullptr, nullptr, nullptr, d_A9, d_kappa, kvar, V, 1.0, d_GA9, d_Gq);
+    }
+    SPDE_LAUNCH_CHECK();
+    return SPDE_OK;
+}
+
+extern "C" int spde_gemv_t(const double *d_B, const double *d_u, int rows, int cols, double *d_out, void *stream)
+{
+    int rc = ensure_scratch();
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nb = 32;
+    if ((long long)cols * nb > 8192) { set_error("spde_gemv_t: too many columns"); return SPDE_ERR_ARG; }
+    k_gemv_t<<<dim3(nb, cols), 256, 0, st>>>(d_B, d_u, rows, cols, g_scratch);
+    k_gemv_final<<<cols, 64, 0, st>>>(g_scratch, nb, d_out);
+    SPDE_LAUNCH_CHECK();
+    return SPDE_OK;
+}

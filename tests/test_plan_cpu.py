@@ -1,0 +1,140 @@
+"""CPU validation of the host-side symbolic analysis and of the device schedules.
+
+The schedules built by libspde_b200.so for the GPU (factorisation, solves, Takahashi) are
+executed by the NumPy interpreter in oracle/plan_emulator.py and compared with dense LAPACK on the
+oracle's Q.  No CUDA call is made here."""
+import numpy as np
+import pytest
+from scipy import sparse
+
+import plan_emulator as pe
+import spde_oracle as so
+from helpers import load_golden, make_oracle
+from spdepy_b200 import _lib
+from spdepy_b200.pattern import Pattern
+
+CASES = ["wm_iso_bc3", "wm_ani_bc1_ext", "varwm_ani_bc2", "ad_ani_bc3_q0", "ad_ha_bc1_q0", "vavd_ani_bc2"]
+
+
+def _setup(name):
+    d = load_golden(name)
+    mod = make_oracle(d)
+    mod.setQ(d["par"])
+    M, N = mod.grid.shape[0], mod.grid.shape[1]
+    T = mod.grid.T if mod.spec.timed else 1
+    plan = _lib.PlanHandle(M, N, T, d["bc"])
+    pat = Pattern(M, N, T, d["bc"])
+    return d, mod, plan, pat
+
+
+def _dense_sym(Q):
+    A = sparse.tril(Q).toarray()
+    return A + np.tril(A, -1).T
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_pattern_roundtrip(name):
+    d, mod, plan, pat = _setup(name)
+    flat = pat.from_sparse(mod.Q)
+    back = pat.to_csc(flat)
+    assert abs(back - mod.Q).max() == 0.0
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_symbolic_structure(name):
+    d, mod, plan, pat = _setup(name)
+    perm = plan.perm.astype(np.int64)
+    assert sorted(perm.tolist()) == list(range(plan.n))
+    first, rowptr, rows, parent = plan.supernodes()
+    # boolean symbolic factorisation of the permuted mesh pattern
+    S = (pat.to_csc(np.ones(pat.nslots * pat.n)).toarray() != 0)[np.ix_(perm, perm)]
+    n = plan.n
+    Lb = np.tril(S)
+    for j in range(n):
+        r = np.nonzero(Lb[j + 1:, j])[0] + j + 1
+        if r.size:
+            Lb[np.ix_(r, r)] |= True
+    Lb = np.tril(Lb)
+    cc = Lb.sum(axis=0)
+    assert int(cc.sum()) == plan.info(2)
+    assert abs(float((cc.astype(float) ** 2).sum()) - plan.info_d(3)) < 0.5
+    # every column's structure must be inside its supernode's (relaxed supernodes may add zeros)
+    for s in range(first.size - 1):
+        below = set(rows[rowptr[s]:rowptr[s + 1]].tolist())
+        for j in range(first[s], first[s + 1]):
+            r = np.nonzero(Lb[:, j])[0]
+            r = r[r >= first[s + 1]]
+            assert set(r.tolist()) <= below
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_emulated_factor_solve_selinv(name):
+    d, mod, plan, pat = _setup(name)
+    n = plan.n
+    flat = pat.from_sparse(mod.Q)
+    em = pe.Emulator(plan)
+    rng = np.random.default_rng(0)
+    cnt = np.zeros(n)
+    cnt[rng.choice(n, n // 3, replace=False)] = 1.0
+    tau = 7.0
+    A = _dense_sym(mod.Q) + np.diag(cnt * tau)
+    assert em.factorize(flat, cnt, tau) == 0
+    sign, ld = np.linalg.slogdet(A)
+    assert abs(em.logdet() - ld) < 1e-10 * abs(ld)
+    perm = plan.perm.astype(np.int64)
+    Lref = np.linalg.cholesky(A[np.ix_(perm, perm)])
+    B = rng.normal(size=(n, 3))
+    X = em.solve(B, mode=0)
+    assert np.abs(X - np.linalg.solve(A, B)).max() < 1e-9 * np.abs(X).max()
+    Zs = em.solve(B, mode=1)        # P^T L^-T z   (model.py:80)
+    ref = np.empty_like(B)
+    ref[perm] = np.linalg.solve(Lref.T, B)
+    assert np.abs(Zs - ref).max() < 1e-9 * np.abs(ref).max()
+    Y = em.solve(B, mode=2)         # L^-1 P b
+    assert np.abs(Y - np.linalg.solve(Lref, B[perm])).max() < 1e-9 * np.abs(Y).max()
+    X1 = em.solve(B[:, 0], mode=0)  # odd number of right-hand sides
+    assert np.abs(X1[:, 0] - X[:, 0]).max() < 1e-12 * np.abs(X).max()
+    # Takahashi selected inverse against the dense inverse on the pattern of Q
+    Zq = em.selinv()
+    Zd = np.linalg.inv(A)
+    full = pat.to_csc(Zq).toarray()
+    mask = pat.to_csc(np.ones(pat.nslots * n)).toarray() != 0
+    assert np.abs(full[mask] - Zd[mask]).max() < 1e-9 * np.abs(Zd).max()
+
+
+def test_not_spd_is_reported():
+    d, mod, plan, pat = _setup("wm_iso_bc3")
+    flat = pat.from_sparse(mod.Q)
+    flat[(pat.nslots // 2) * plan.n + 5] = -1.0     # a negative diagonal entry
+    em = pe.Emulator(plan)
+    assert em.factorize(flat) != 0
+
+
+@pytest.mark.parametrize("shape", [(24, 22, 9, 3), (40, 37, 1, 1), (21, 20, 6, 2)])
+def test_emulated_large_fronts(shape):
+    """Synthetic SPD matrix on the mesh pattern, big enough for multi-block supernodes
+    (nc > 256 exercises the outer right-looking blocks)."""
+    M, N, T, bc = shape
+    plan = _lib.PlanHandle(M, N, T, bc)
+    assert plan.info(13) > (256 if T > 1 else 64)
+    pat = Pattern(M, N, T, bc)
+    n = plan.n
+    rng = np.random.default_rng(1)
+    W = pat.to_csc(rng.normal(size=pat.nslots * n))
+    A = (W + W.T) * 0.5
+    A = A + sparse.diags(np.abs(A).sum(axis=1).A1 + 1.0)
+    A = sparse.csc_matrix(A)
+    flat = pat.from_sparse(A)
+    em = pe.Emulator(plan)
+    assert em.factorize(flat) == 0
+    Ad = A.toarray()
+    sign, ld = np.linalg.slogdet(Ad)
+    assert abs(em.logdet() - ld) < 1e-11 * abs(ld)
+    B = rng.normal(size=(n, 2))
+    X = em.solve(B, mode=0)
+    assert np.abs(Ad @ X - B).max() < 1e-10 * np.abs(B).max()
+    Zq = em.selinv()
+    Zd = np.linalg.inv(Ad)
+    full = pat.to_csc(Zq).toarray()
+    mask = pat.to_csc(np.ones(pat.nslots * n)).toarray() != 0
+    assert np.abs(full[mask] - Zd[mask]).max() < 1e-10 * np.abs(Zd).max()
