@@ -121,9 +121,10 @@ int spde_factor_info(spde_plan *p, int which, int *h_status, int *h_bad_column);
 int spde_logdet(spde_plan *p, int which, double *h_logdet, void *stream);
 
 /* ------------------------------------------------------------------ solves (K7) */
-/* X is n x k, ROW-major on the device (node-major: the k values of a node are contiguous), in the
- * ORIGINAL node ordering; solved in place.  mode 0: A x = b (solve_A); 1: L^T (P x) = b then P^T
- * (solve_Lt + apply_Pt, model.py:80); 2: L y = P b (solve_L + apply_P). */
+/* X is n x k, ROW-major on the device (node-major: the k values of a node are contiguous); solved
+ * in place.  mode is a bit set: 1 forward substitution with L, 2 back substitution with L^T,
+ * 4 apply P to the input (rows taken in the original node ordering), 8 apply P^T to the output.
+ * solve_A = 15, solve_Lt = 2, solve_L = 1, apply_Pt(solve_Lt(z)) = 10 (model.py:80). */
 int spde_solve(spde_plan *p, int which, int mode, double *d_X, int k, void *stream);
 
 /* ------------------------------------------------------------------ selected inverse (K10) */
@@ -136,6 +137,16 @@ int spde_selinv(spde_plan *p, int which, double *d_Zq, void *stream);
 int spde_q_apply(int M, int N, int T, int bc, const double *d_Q, const double *d_X, int k, double *d_Y, void *stream);
 /* h_out[0] = sum(X .* Y) over n*k entries (deterministic two-stage reduction). */
 int spde_dot(const double *d_X, const double *d_Y, int64_t len, double *h_out, void *stream);
+/* h_out[0] = sum_node w[node] * sum_p X[node,p]*Y[node,p] (X, Y row-major n x k). */
+int spde_wdot(const double *d_X, const double *d_Y, const double *d_w, int64_t n, int k, double *h_out, void *stream);
+/* h_out[0] = sum_{i,p} (data[i,p] - mu[obs[i],p])^2; data nobs x r, mu n x r, both row-major
+ * (advection_diffusion2D.py:198). */
+int spde_residual_ss(const double *d_data, const double *d_mu, const int64_t *d_obs, int64_t nobs, int r,
+                     double *h_out, void *stream);
+/* b[obs[i],:] += tau * data[i,:]   (b = S^T data * tau, advection_diffusion2D.py:194; b zeroed by the caller). */
+int spde_scatter_obs(const double *d_data, const int64_t *d_obs, int64_t nobs, int r, double tau, double *d_b, void *stream);
+/* d_Qdiag[node] += tau * cnt[node]: Q + tau S^T S on the diagonal slot (model.py:120-124). */
+int spde_add_diag(double *d_Qdiag, const double *d_cnt, double tau, int64_t n, void *stream);
 /* W[slot,node] (+)= alpha * sum_p X[node,p] * Y[nbr(node,slot),p]  (sampled dense-dense product on the
  * pattern of Q; the Hutchinson weights of advection_diffusion2D.py:204-206). */
 int spde_sddmm(int M, int N, int T, int bc, const double *d_X, const double *d_Y, int k, double alpha,
@@ -151,6 +162,14 @@ int spde_assembly_adjoint(int M, int N, int T, int bc, const double *d_W, const 
                           double *d_work, double *d_GA9, double *d_Gq, double *d_GQ0_25, void *stream);
 /* d_out[c] = sum_r B[r,c] * u[r], B row-major rows x cols (spline-basis chain rule, evalB/evalBH). */
 int spde_gemv_t(const double *d_B, const double *d_u, int rows, int cols, double *d_out, void *stream);
+
+/* One dense task through the grouped FP64 tensor-core GEMM (unit test + roofline probe).
+ * cfg 0: 128x128 tiles, 1: 128x64, 2: 64x64; a_kmaj/b_kmaj: operand stored with K contiguous;
+ * flags: GF_* bits of csrc/gemm.cuh (lower 1<<9, beta0 1<<10, neg 1<<11).  *h_ms = mean device time
+ * of `reps` launches after one warm-up launch. */
+int spde_gemm_single(int cfg, int a_kmaj, int b_kmaj, int flags, int M, int N, int K,
+                     const double *d_A, int lda, const double *d_B, int ldb, double *d_C, int ldc,
+                     int reps, float *h_ms, void *stream);
 
 #ifdef __cplusplus
 }

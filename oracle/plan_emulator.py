@@ -225,22 +225,22 @@ class Emulator:
     def logdet(self):
         return 2.0 * np.log(self.sp[0][self.diagpos]).sum()
 
-    def solve(self, X, mode=0):
+    def solve(self, X, mode=15):
         """``spde_solve`` on a row-major (n,k) array (returns a new array)."""
         X = np.asarray(X, dtype=np.float64)
         X = X.reshape(self.n, -1)
         k = X.shape[1]
         kp = k + (k & 1)
         Xp = np.zeros((self.n, kp))
-        Xp[:, :k] = X[self.perm] if mode != 1 else X
+        Xp[:, :k] = X[self.perm] if mode & 4 else X
         self.sp[4] = Xp.reshape(-1).copy()
-        if mode in (0, 2):
+        if mode & 1:
             self.run(Program(self.plan, 1, k))
-        if mode in (0, 1):
+        if mode & 2:
             self.run(Program(self.plan, 2, k))
         Xp = self.sp[4].reshape(self.n, kp)[:, :k]
         out = np.empty_like(Xp)
-        if mode != 2:
+        if mode & 8:
             out[self.perm] = Xp
         else:
             out[:] = Xp

@@ -56,9 +56,15 @@ _SIGS = {
     "spde_selinv": (c_int, [c_vp, c_int, c_vp, c_vp]),
     "spde_q_apply": (c_int, [c_int, c_int, c_int, c_int, c_vp, c_vp, c_int, c_vp, c_vp]),
     "spde_dot": (c_int, [c_vp, c_vp, c_i64, ctypes.POINTER(c_dbl), c_vp]),
+    "spde_wdot": (c_int, [c_vp, c_vp, c_vp, c_i64, c_int, ctypes.POINTER(c_dbl), c_vp]),
+    "spde_residual_ss": (c_int, [c_vp, c_vp, c_vp, c_i64, c_int, ctypes.POINTER(c_dbl), c_vp]),
+    "spde_scatter_obs": (c_int, [c_vp, c_vp, c_i64, c_int, c_dbl, c_vp, c_vp]),
+    "spde_add_diag": (c_int, [c_vp, c_vp, c_dbl, c_i64, c_vp]),
     "spde_sddmm": (c_int, [c_int, c_int, c_int, c_int, c_vp, c_vp, c_int, c_dbl, c_int, c_vp, c_vp]),
     "spde_assembly_adjoint": (c_int, [c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_int, c_dbl, c_dbl, c_dbl, c_int,
                                       c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "spde_gemm_single": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_int, c_vp, c_int, c_vp, c_int,
+                                 c_int, ctypes.POINTER(ctypes.c_float), c_vp]),
     "spde_gemv_t": (c_int, [c_vp, c_vp, c_int, c_int, c_vp, c_vp]),
 }
 

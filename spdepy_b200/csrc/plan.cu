@@ -532,7 +532,7 @@ extern "C" int spde_logdet(spde_plan *pp, int which, double *h_logdet, void *str
 extern "C" int spde_solve(spde_plan *pp, int which, int mode, double *d_X, int k, void *stream)
 {
     Plan &p = *reinterpret_cast<Plan *>(pp);
-    if (!p.factored[which] || k < 1 || mode < 0 || mode > 2) { set_error("spde_solve: bad state/arguments"); return SPDE_ERR_ARG; }
+    if (!p.factored[which] || k < 1 || mode < 1 || mode > 15 || !(mode & 3)) { set_error("spde_solve: bad state/arguments"); return SPDE_ERR_ARG; }
     cudaStream_t st = (cudaStream_t)stream;
     const int n = p.sym.n, kp = k + (k & 1);
     const int64_t need = (int64_t)n * kp;
@@ -544,12 +544,12 @@ extern "C" int spde_solve(spde_plan *pp, int which, int mode, double *d_X, int k
         p.x_cap = need;
     }
     const int grid = 148 * 8;
-    k_perm_in<<<grid, 256, 0, st>>>(d_X, p.d_perm, n, k, kp, mode != 1, p.d_X);
+    k_perm_in<<<grid, 256, 0, st>>>(d_X, p.d_perm, n, k, kp, (mode >> 2) & 1, p.d_X);
     SPDE_LAUNCH_CHECK();
     int rc;
-    if (mode == 0 || mode == 2) { rc = run_program(p, p.solve_program(k, 0), which, st, nullptr); if (rc) return rc; }
-    if (mode == 0 || mode == 1) { rc = run_program(p, p.solve_program(k, 1), which, st, nullptr); if (rc) return rc; }
-    k_perm_out<<<grid, 256, 0, st>>>(p.d_X, p.d_perm, n, k, kp, mode != 2, d_X);
+    if (mode & 1) { rc = run_program(p, p.solve_program(k, 0), which, st, nullptr); if (rc) return rc; }
+    if (mode & 2) { rc = run_program(p, p.solve_program(k, 1), which, st, nullptr); if (rc) return rc; }
+    k_perm_out<<<grid, 256, 0, st>>>(p.d_X, p.d_perm, n, k, kp, (mode >> 3) & 1, d_X);
     SPDE_LAUNCH_CHECK();
     return SPDE_OK;
 }
@@ -569,4 +569,57 @@ extern "C" int spde_selinv(spde_plan *pp, int which, double *d_Zq, void *stream)
     }
     SPDE_CUDA_CHECK(cudaMemsetAsync(d_Zq, 0, (size_t)p.sym.nslots * p.sym.n * sizeof(double), st));
     return run_program(p, p.selinv, which, st, d_Zq);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Single dense task through the grouped GEMM kernel: unit test and FP64 roofline probe.
+// C (M x N, ldc) (op)= +-A*B with the flag/variant semantics of gemm.cuh; returns the mean device
+// time of `reps` launches (CUDA events on `stream`) in *h_ms.
+extern "C" int spde_gemm_single(int cfg, int a_kmaj, int b_kmaj, int flags, int M, int N, int K,
+                                const double *d_A, int lda, const double *d_B, int ldb, double *d_C, int ldc,
+                                int reps, float *h_ms, void *stream)
+{
+    if (cfg < 0 || cfg > 2 || M < 1 || N < 1 || K < 1) { set_error("spde_gemm_single: bad arguments"); return SPDE_ERR_ARG; }
+    cudaStream_t st = (cudaStream_t)stream;
+    static const int BMs[3] = {128, 128, 64}, BNs[3] = {128, 64, 64};
+    Program P;
+    GemmTask t;
+    memset(&t, 0, sizeof t);
+    t.lda = lda; t.ldb = ldb; t.ldc = ldc; t.M = M; t.N = N; t.K = K;
+    t.flags = (flags & ~511) | 0 | (1 << 3) | (2 << 6);
+    P.gemm.push_back(t);
+    const int tm = (M + BMs[cfg] - 1) / BMs[cfg], tn = (N + BNs[cfg] - 1) / BNs[cfg];
+    for (int tj = 0; tj < tn; tj++)
+        for (int ti = 0; ti < tm; ti++) {
+            if ((flags & GF_LOWER) && (ti + 1) * BMs[cfg] - 1 < tj * BNs[cfg]) continue;
+            P.tiles.push_back(TileRef{0, ti, tj, 0});
+        }
+    int rc = upload_program(P);
+    if (rc) return rc;
+    GemmSpaces sp;
+    memset(&sp, 0, sizeof sp);
+    sp.base[0] = const_cast<double *>(d_A);
+    sp.base[1] = const_cast<double *>(d_B);
+    sp.base[2] = d_C;
+    Launch L;
+    memset(&L, 0, sizeof L);
+    L.kind = LK_GEMM; L.variant = cfg * 4 + (a_kmaj ? 2 : 0) + (b_kmaj ? 1 : 0);
+    L.ntasks = 1; L.ntiles = (int)P.tiles.size();
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaError_t err = launch_gemm(L, P, sp, st);   // warm-up / the tested launch when reps == 0
+    cudaEventRecord(e0, st);
+    for (int i = 0; i < reps && err == cudaSuccess; i++) err = launch_gemm(L, P, sp, st);
+    cudaEventRecord(e1, st);
+    cudaError_t e2 = cudaStreamSynchronize(st);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (h_ms) *h_ms = reps > 0 ? ms / reps : 0.f;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    free_program(P);
+    if (err != cudaSuccess || e2 != cudaSuccess) {
+        set_error(std::string("spde_gemm_single: ") + cudaGetErrorString(err != cudaSuccess ? err : e2));
+        return SPDE_ERR_CUDA;
+    }
+    return SPDE_OK;
 }

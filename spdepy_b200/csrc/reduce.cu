@@ -60,6 +60,49 @@ __global__ void k_dot_partial(const double *__restrict__ X, const double *__rest
     s = block_sum(s, sh);
     if (threadIdx.x == 0) partial[blockIdx.x] = s;
 }
+// sum_node w[node] * sum_p X[node,p]*Y[node,p]   (tau-gradient of advection_diffusion2D.py:207)
+__global__ void k_wdot_partial(const double *__restrict__ X, const double *__restrict__ Y, const double *__restrict__ w,
+                               long long n, int k, double *__restrict__ partial)
+{
+    __shared__ double sh[32];
+    const long long len = n * k;
+    double s = 0.0;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < len; e += (long long)gridDim.x * blockDim.x)
+        s += w[e / k] * X[e] * Y[e];
+    s = block_sum(s, sh);
+    if (threadIdx.x == 0) partial[blockIdx.x] = s;
+}
+// sum (data[i,p] - mu[obs[i],p])^2   (advection_diffusion2D.py:198)
+__global__ void k_resid_partial(const double *__restrict__ data, const double *__restrict__ mu, const long long *__restrict__ obs,
+                                long long nobs, int r, double *__restrict__ partial)
+{
+    __shared__ double sh[32];
+    const long long len = nobs * r;
+    double s = 0.0;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < len; e += (long long)gridDim.x * blockDim.x) {
+        const long long i = e / r;
+        const int p = (int)(e % r);
+        const double d = data[e] - mu[obs[i] * r + p];
+        s += d * d;
+    }
+    s = block_sum(s, sh);
+    if (threadIdx.x == 0) partial[blockIdx.x] = s;
+}
+// b[obs[i], :] += data[i, :] * tau   (S^T data * tau, advection_diffusion2D.py:194)
+__global__ void k_scatter_obs(const double *__restrict__ data, const long long *__restrict__ obs, long long nobs, int r,
+                              double tau, double *__restrict__ b)
+{
+    const long long len = nobs * r;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < len; e += (long long)gridDim.x * blockDim.x)
+        atomicAdd(&b[obs[e / r] * r + e % r], data[e] * tau);
+}
+// diag slot of Q += tau * cnt   (Model.update, model.py:120-124)
+__global__ void k_add_diag(double *__restrict__ Qdiag, const double *__restrict__ cnt, double tau, long long n)
+{
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x)
+        Qdiag[e] += cnt[e] * tau;
+}
+
 __global__ void k_final(const double *__restrict__ partial, int m, double *__restrict__ out)
 {
     __shared__ double sh[32];
@@ -277,6 +320,52 @@ extern "C" int spde_gemv_t(const double *d_B, const double *d_u, int rows, int c
     if ((long long)cols * nb > 8192) { set_error("spde_gemv_t: too many columns"); return SPDE_ERR_ARG; }
     k_gemv_t<<<dim3(nb, cols), 256, 0, st>>>(d_B, d_u, rows, cols, g_scratch);
     k_gemv_final<<<cols, 64, 0, st>>>(g_scratch, nb, d_out);
+    SPDE_LAUNCH_CHECK();
+    return SPDE_OK;
+}
+
+static int finish_sum(double *h_out, cudaStream_t st, int nb)
+{
+    k_final<<<1, 1024, 0, st>>>(g_scratch, nb, g_scratch + nb);
+    SPDE_LAUNCH_CHECK();
+    SPDE_CUDA_CHECK(cudaMemcpyAsync(h_out, g_scratch + nb, sizeof(double), cudaMemcpyDeviceToHost, st));
+    SPDE_CUDA_CHECK(cudaStreamSynchronize(st));
+    return SPDE_OK;
+}
+
+extern "C" int spde_wdot(const double *d_X, const double *d_Y, const double *d_w, int64_t n, int k, double *h_out, void *stream)
+{
+    int rc = ensure_scratch();
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nb = 1184;
+    k_wdot_partial<<<nb, 256, 0, st>>>(d_X, d_Y, d_w, n, k, g_scratch);
+    return finish_sum(h_out, st, nb);
+}
+
+extern "C" int spde_residual_ss(const double *d_data, const double *d_mu, const int64_t *d_obs, int64_t nobs, int r,
+                                double *h_out, void *stream)
+{
+    int rc = ensure_scratch();
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nb = 1184;
+    k_resid_partial<<<nb, 256, 0, st>>>(d_data, d_mu, (const long long *)d_obs, nobs, r, g_scratch);
+    return finish_sum(h_out, st, nb);
+}
+
+extern "C" int spde_scatter_obs(const double *d_data, const int64_t *d_obs, int64_t nobs, int r, double tau, double *d_b, void *stream)
+{
+    const long long len = (long long)nobs * r;
+    k_scatter_obs<<<(int)std::min<long long>((len + 255) / 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(
+        d_data, (const long long *)d_obs, nobs, r, tau, d_b);
+    SPDE_LAUNCH_CHECK();
+    return SPDE_OK;
+}
+
+extern "C" int spde_add_diag(double *d_Qdiag, const double *d_cnt, double tau, int64_t n, void *stream)
+{
+    k_add_diag<<<(int)std::min<long long>((n + 255) / 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(d_Qdiag, d_cnt, tau, n);
     SPDE_LAUNCH_CHECK();
     return SPDE_OK;
 }

@@ -1,0 +1,249 @@
+"""Device engine: thin, stateful Python over the C ABI (``include/spde_b200.h``).
+
+One :class:`Engine` per (mesh shape, boundary condition).  It owns the symbolic plan (created
+lazily, once per mesh -- the reference re-analyses on every ``cholesky`` call,
+``advection_diffusion2D.py:117,193``), the fixed sparsity pattern, and convenience wrappers that
+take/return ``torch.cuda.DoubleTensor`` buffers.  PyTorch is used for device memory and streams
+only; every numeric step is a kernel of ``libspde_b200.so``.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import check, lib, ptr
+from .pattern import Pattern
+
+F64 = torch.float64
+
+
+def _dev():
+    if not torch.cuda.is_available():
+        raise _lib.SpdeError("spdepy_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def to_dev(a, dtype=F64) -> torch.Tensor:
+    if isinstance(a, torch.Tensor):
+        return a.to(device=_dev(), dtype=dtype).contiguous()
+    return torch.as_tensor(np.ascontiguousarray(a), dtype=dtype, device=_dev())
+
+
+class Factor:
+    """Drop-in for the ``sksparse.cholmod.Factor`` methods the reference uses
+    (``advection_diffusion2D.py:194-202``, ``model.py:80,126``): ``logdet, solve_A, solve_Lt,
+    solve_L, apply_P, apply_Pt, P``.  NumPy in -> NumPy out, torch CUDA in -> torch CUDA out.
+    The factor lives in store ``which`` of the engine's plan and stays valid until that store is
+    refactorised."""
+
+    def __init__(self, engine: "Engine", which: int):
+        self.engine = engine
+        self.which = which
+        self.serial = engine.serial[which]
+
+    def _alive(self):
+        if self.engine.serial[self.which] != self.serial:
+            raise _lib.SpdeError("this factor has been overwritten by a later factorisation")
+
+    def P(self) -> np.ndarray:
+        return self.engine.plan.perm.copy()
+
+    def logdet(self) -> float:
+        self._alive()
+        return self.engine.logdet(self.which)
+
+    def _solve(self, b, mode):
+        self._alive()
+        is_np = not isinstance(b, torch.Tensor)
+        if is_np and hasattr(b, "toarray"):
+            b = b.toarray()
+        x = to_dev(np.asarray(b, dtype=np.float64) if is_np else b).clone()
+        one_d = x.dim() == 1
+        x = x.reshape(self.engine.n, -1).contiguous()
+        self.engine.solve(self.which, x, mode)
+        if one_d:
+            x = x.reshape(-1)
+        return x.cpu().numpy() if is_np else x
+
+    def solve_A(self, b):
+        return self._solve(b, 15)
+
+    __call__ = solve_A
+
+    def solve_Lt(self, b, use_LDLt_decomposition=False):
+        return self._solve(b, 2)
+
+    def solve_L(self, b, use_LDLt_decomposition=False):
+        return self._solve(b, 1)
+
+    def apply_P(self, x):
+        p = self.engine.plan.perm
+        return x[torch.as_tensor(p, device=x.device, dtype=torch.long)] if isinstance(x, torch.Tensor) else np.asarray(x)[p]
+
+    def apply_Pt(self, x):
+        p = self.engine.plan.perm
+        if isinstance(x, torch.Tensor):
+            out = torch.empty_like(x)
+            out[torch.as_tensor(p, device=x.device, dtype=torch.long)] = x
+            return out
+        x = np.asarray(x)
+        out = np.empty_like(x)
+        out[p] = x
+        return out
+
+
+class Engine:
+    _cache: dict = {}
+
+    @classmethod
+    def get(cls, M: int, N: int, T: int, bc: int) -> "Engine":
+        key = (M, N, T, bc, torch.cuda.current_device() if torch.cuda.is_available() else -1)
+        if key not in cls._cache:
+            cls._cache[key] = cls(M, N, T, bc)
+        return cls._cache[key]
+
+    def __init__(self, M: int, N: int, T: int, bc: int):
+        self.M, self.N, self.T, self.bc = M, N, T, bc
+        self.Ns = M * N
+        self.n = self.Ns * T
+        self.nslots = 25 if T == 1 else 43
+        self._plan = None
+        self._pattern = None
+        self.serial = [0, 0]
+
+    @property
+    def plan(self) -> _lib.PlanHandle:
+        if self._plan is None:
+            self._plan = _lib.PlanHandle(self.M, self.N, self.T, self.bc)
+        return self._plan
+
+    @property
+    def pattern(self) -> Pattern:
+        if self._pattern is None:
+            self._pattern = Pattern(self.M, self.N, self.T, self.bc)
+        return self._pattern
+
+    # ------------------------------------------------------------------ assembly (K2, K3)
+    def ah_stencil(self, hx, hy, H: torch.Tensor, face: bool) -> torch.Tensor:
+        out = torch.empty(9 * self.Ns, dtype=F64, device=_dev())
+        check(lib.spde_ah_stencil(self.M, self.N, self.bc, hx, hy, ptr(H), int(face), ptr(out), _stream()))
+        return out
+
+    def aw_stencil(self, hx, hy, G: torch.Tensor, dG, face: bool, diff: int, nan_to_zero: bool) -> torch.Tensor:
+        out = torch.empty(9 * self.Ns, dtype=F64, device=_dev())
+        check(lib.spde_aw_stencil(self.M, self.N, self.bc, hx, hy, ptr(G), ptr(dG), int(face), diff, int(nan_to_zero),
+                                  ptr(out), _stream()))
+        return out
+
+    def combine_A(self, flavour: int, V, dt, kappa: torch.Tensor, ah, aw) -> torch.Tensor:
+        out = torch.empty(9 * self.Ns, dtype=F64, device=_dev())
+        kvar = int(kappa is not None and kappa.numel() > 1)
+        check(lib.spde_combine_A(self.Ns, flavour, V, dt, ptr(kappa), kvar, ptr(ah), ptr(aw), ptr(out), _stream()))
+        return out
+
+    def atda(self, A9: torch.Tensor, kappa: torch.Tensor, V, mode: int) -> torch.Tensor:
+        out = torch.empty(25 * self.Ns, dtype=F64, device=_dev())
+        check(lib.spde_atda(self.M, self.N, self.bc, ptr(A9), ptr(kappa), int(kappa.numel() > 1), V, mode, ptr(out), _stream()))
+        return out
+
+    def fill_spacetime(self, AtDA, A9, kappa, V, Q0_25, sigma, dt, divide: bool) -> torch.Tensor:
+        out = torch.empty(43 * self.n, dtype=F64, device=_dev())
+        check(lib.spde_fill_spacetime(self.M, self.N, self.T, self.bc, ptr(AtDA), ptr(A9), ptr(kappa), int(kappa.numel() > 1),
+                                      V, ptr(Q0_25), sigma, dt, int(divide), ptr(out), _stream()))
+        return out
+
+    # ------------------------------------------------------------------ factor / solve / selinv (K4-K7, K10)
+    def factorize(self, which: int, Q: torch.Tensor, cnt=None, tau: float = 0.0) -> Factor:
+        self.serial[which] += 1
+        check(lib.spde_factorize(self.plan.h, which, ptr(Q), ptr(cnt), float(tau), _stream()))
+        return Factor(self, which)
+
+    def logdet(self, which: int) -> float:
+        out = ctypes.c_double()
+        check(lib.spde_logdet(self.plan.h, which, ctypes.byref(out), _stream()))
+        return out.value
+
+    def solve(self, which: int, X: torch.Tensor, mode: int = 15) -> torch.Tensor:
+        assert X.is_cuda and X.dtype == F64 and X.is_contiguous() and X.shape[0] == self.n
+        check(lib.spde_solve(self.plan.h, which, mode, ptr(X), X.shape[1] if X.dim() > 1 else 1, _stream()))
+        return X
+
+    def selinv(self, which: int) -> torch.Tensor:
+        Z = torch.empty(self.nslots * self.n, dtype=F64, device=_dev())
+        check(lib.spde_selinv(self.plan.h, which, ptr(Z), _stream()))
+        return Z
+
+    # ------------------------------------------------------------------ reductions (K8, K9, K11)
+    def q_apply(self, Q: torch.Tensor, X: torch.Tensor) -> torch.Tensor:
+        Y = torch.empty_like(X)
+        check(lib.spde_q_apply(self.M, self.N, self.T, self.bc, ptr(Q), ptr(X), X.shape[1], ptr(Y), _stream()))
+        return Y
+
+    @staticmethod
+    def dot(X: torch.Tensor, Y: torch.Tensor) -> float:
+        out = ctypes.c_double()
+        check(lib.spde_dot(ptr(X), ptr(Y), X.numel(), ctypes.byref(out), _stream()))
+        return out.value
+
+    @staticmethod
+    def wdot(X: torch.Tensor, Y: torch.Tensor, w: torch.Tensor) -> float:
+        out = ctypes.c_double()
+        check(lib.spde_wdot(ptr(X), ptr(Y), ptr(w), X.shape[0], X.shape[1], ctypes.byref(out), _stream()))
+        return out.value
+
+    @staticmethod
+    def residual_ss(data: torch.Tensor, mu: torch.Tensor, obs: torch.Tensor) -> float:
+        out = ctypes.c_double()
+        check(lib.spde_residual_ss(ptr(data), ptr(mu), ptr(obs), data.shape[0], data.shape[1], ctypes.byref(out), _stream()))
+        return out.value
+
+    def scatter_obs(self, data: torch.Tensor, obs: torch.Tensor, tau: float) -> torch.Tensor:
+        b = torch.zeros(self.n, data.shape[1], dtype=F64, device=_dev())
+        check(lib.spde_scatter_obs(ptr(data), ptr(obs), data.shape[0], data.shape[1], float(tau), ptr(b), _stream()))
+        return b
+
+    def add_diag(self, Q: torch.Tensor, cnt: torch.Tensor, tau: float) -> None:
+        diag = Q[(self.nslots // 2) * self.n:(self.nslots // 2 + 1) * self.n]
+        check(lib.spde_add_diag(ptr(diag), ptr(cnt), float(tau), self.n, _stream()))
+
+    def sddmm(self, X: torch.Tensor, Y: torch.Tensor, alpha: float, W=None) -> torch.Tensor:
+        acc = W is not None
+        if W is None:
+            W = torch.zeros(self.nslots * self.n, dtype=F64, device=_dev())
+        check(lib.spde_sddmm(self.M, self.N, self.T, self.bc, ptr(X), ptr(Y), X.shape[1], float(alpha), int(acc), ptr(W), _stream()))
+        return W
+
+    def assembly_adjoint(self, W, A9, kappa, V, sigma, dt, timed: bool):
+        Ns = self.Ns
+        GA = torch.empty(9 * Ns, dtype=F64, device=_dev())
+        if timed:
+            work = torch.empty(44 * Ns, dtype=F64, device=_dev())
+            Gq = torch.empty(Ns, dtype=F64, device=_dev())
+            GQ0 = torch.empty(25 * Ns, dtype=F64, device=_dev())
+        else:
+            work = Gq = GQ0 = None
+        check(lib.spde_assembly_adjoint(self.M, self.N, self.T if timed else 1, self.bc, ptr(W), ptr(A9), ptr(kappa),
+                                        int(kappa.numel() > 1), V, sigma, dt, int(timed), ptr(work), ptr(GA), ptr(Gq),
+                                        ptr(GQ0), _stream()))
+        return GA, Gq, GQ0
+
+    @staticmethod
+    def gemv_t(B: torch.Tensor, u: torch.Tensor) -> torch.Tensor:
+        out = torch.empty(B.shape[1], dtype=F64, device=_dev())
+        check(lib.spde_gemv_t(ptr(B), ptr(u), B.shape[0], B.shape[1], ptr(out), _stream()))
+        return out
+
+    # ------------------------------------------------------------------ export
+    def to_scipy(self, Q: torch.Tensor):
+        """slot layout -> canonical SciPy CSC (what the reference exposes as ``mod.Q``); exact zeros
+        are dropped, as SciPy's SpGEMM / sparse add do in the reference."""
+        m = self.pattern.to_csc(Q.cpu().numpy())
+        m.eliminate_zeros()
+        return m

@@ -1,0 +1,72 @@
+"""Model classes with the reference's names and ``spde_init`` dispatcher (``spdes/__init__.py:1-105``).
+
+Every class is a configuration of :class:`spdepy_b200.spdes.base.SPDE2D`; the table below is the
+reference's App. B parameter layout.  Families that are not wired yet raise
+``NotImplementedError`` at construction instead of silently doing something else."""
+from .base import SPDE2D
+
+N9 = 9
+
+
+def _cls(pyname, typename, **cfg):
+    return type(pyname, (SPDE2D,), dict(name=typename, **cfg))
+
+
+# spatial Whittle-Matern (whittle_matern2D.py, whittle_matern_anisotropic2D.py, whittle_matern_ha2D.py)
+WhittleMatern2D = _cls("WhittleMatern2D", "whittle-matern-isotropic-2D", Hkind="iso", default_own=(-1, -1))
+WhittleMaternAnisotropic2D = _cls("WhittleMaternAnisotropic2D", "whittle-matern-anisotropic-2D", Hkind="aniso",
+                                  default_own=(-1, -1, 0.1, 0.1))
+WhittleMaternHa2D = _cls("WhittleMaternHa2D", "whittle-matern-ha-2D", Hkind="ha", default_own=(-1, -1, 0.1, 0.1))
+VarWhittleMaternAnisotropic2D = _cls("VarWhittleMaternAnisotropic2D", "var-whittle-matern-anisotropic-2D", kvar=True,
+                                     Hkind="aniso", Hvar=True, default_own=([-1] * N9, [-1] * N9, [0.1] * N9, [0.1] * N9))
+# advection-diffusion, constant coefficients (advection_*diffusion2D.py)
+AdvectionDiffusion2D = _cls("AdvectionDiffusion2D", "advection-diffusion-2D", timed=True, Hkind="aniso", wkind="const",
+                            aflav=1, default_own=(-1, -1, 0.01, 0.01, 0.01, 0.01, 0))
+AdvectionIDiffusion2D = _cls("AdvectionIDiffusion2D", "advection-idiffusion-2D", timed=True, Hkind="iso", wkind="const",
+                             aflav=1, default_own=(-1, -1, 0.1, 0.1, 0))
+AdvectionHaDiffusion2D = _cls("AdvectionHaDiffusion2D", "advection-ha-diffusion-2D", timed=True, Hkind="ha", wkind="const",
+                              aflav=1, default_own=(-1, -1, 0.01, 0.01, 0.01, 0.01, 0))
+# spatially varying diffusion and/or advection
+AdvectionVarDiffusion2D = _cls("AdvectionVarDiffusion2D", "advection-var-diffusion-2D", timed=True, kvar=True, Hkind="aniso",
+                               Hvar=True, wkind="const", aflav=2,
+                               default_own=([-1] * N9, [-1] * N9, [0.1] * N9, [0.1] * N9, 0.1, 0.1, 0))
+AdvectionVarIDiffusion2D = _cls("AdvectionVarIDiffusion2D", "advection-var-idiffusion-2D", timed=True, kvar=True, Hkind="iso",
+                                Hvar=True, wkind="const", aflav=2, default_own=([-1] * N9, [-1] * N9, 0.1, 0.1, 0))
+VarAdvectionDiffusion2D = _cls("VarAdvectionDiffusion2D", "var-advection-diffusion-2D", timed=True, Hkind="aniso",
+                               wkind="var", aflav=2, default_own=(-1, -1, 0.1, 0.1, [0.1] * 18, 0))
+VarAdvectionIDiffusion2D = _cls("VarAdvectionIDiffusion2D", "var-advection-idiffusion-2D", timed=True, Hkind="iso",
+                                wkind="var", aflav=2, default_own=(-1, -1, [0.01] * 18, 0))
+VarAdvectionVarDiffusion2D = _cls("VarAdvectionVarDiffusion2D", "var-advection-var-diffusion-2D", timed=True, kvar=True,
+                                  Hkind="aniso", Hvar=True, wkind="var", aflav=2, divide=True,
+                                  default_own=([-1] * N9, [-1] * N9, [0.1] * 18, [0.1] * 18, 0))
+VarAdvectionVarIDiffusion2D = _cls("VarAdvectionVarIDiffusion2D", "var-advection-var-idiffusion-2D", timed=True, kvar=True,
+                                   Hkind="iso", Hvar=True, wkind="var", aflav=2, divide=True,
+                                   default_own=([-1] * N9, [-1] * N9, [0.1] * 18, 0))
+
+_TABLE = {
+    # model id -> (ha class, anisotropic class, isotropic class)
+    ("whittle-matern", 1): (WhittleMaternHa2D, WhittleMaternAnisotropic2D, WhittleMatern2D),
+    ("var-whittle-matern", -1): (None, VarWhittleMaternAnisotropic2D, None),
+    ("advection-diffusion", 2): (AdvectionHaDiffusion2D, AdvectionDiffusion2D, AdvectionIDiffusion2D),
+    ("advection-var-diffusion", 3): (None, AdvectionVarDiffusion2D, AdvectionVarIDiffusion2D),
+    ("var-advection-diffusion", 6): (None, VarAdvectionDiffusion2D, VarAdvectionIDiffusion2D),
+    ("var-advection-var-diffusion", 7): (None, VarAdvectionVarDiffusion2D, VarAdvectionVarIDiffusion2D),
+}
+_NEXT = {"cov-advection-diffusion": 4, "cov-advection-var-diffusion": 5, "seperable-spatial-temporal": 8}
+
+
+def spde_init(model, grid, parameters=None, ani=True, ha=True, bc=3, mod0=None):
+    if grid.sdim != 2:
+        raise NotImplementedError("Model not implemented for 3D grids")
+    for (name, num), (c_ha, c_ani, c_iso) in _TABLE.items():
+        if model == name or model == num:
+            cls = c_ha if ha else (c_ani if ani else c_iso)
+            if cls is None:
+                raise NotImplementedError("%s with ha=%s, anisotropic=%s is not wired to the B200 path yet "
+                                          "(SURVEY.md section 8f)" % (name, ha, ani))
+            if cls.timed:
+                return cls(par=parameters, grid=grid, bc=bc, mod0=mod0)
+            return cls(par=parameters, grid=grid, bc=bc)
+    if model in _NEXT or model in _NEXT.values():
+        raise NotImplementedError("model family %r is outside this round's hot-path scope (SURVEY.md section 8f)" % (model,))
+    raise AssertionError("Model not implemented")

@@ -1,0 +1,408 @@
+"""SPDE model classes on the B200 engine -- one parametrised implementation behind the reference's
+per-class API (``__init__(grid,[mod0],par,bc)``, ``getPars/setPars/initFit/setQ/makeQ/logLike/print/
+Ah/Aw``; attributes ``Q, Q_fac, S, data, r, tau, type, mod0``).
+
+What a class of the reference does with ``scipy.sparse`` + CHOLMOD per call
+(``advection_diffusion2D.py:86-223``) happens here on the device:
+
+  fields (host NumPy, as in the reference) -> K2 stencils -> K3 assembly into the slot layout
+  -> K4/K5 supernodal Cholesky of Q and of Q + tau S^T S -> K6 logdet, K7 solves, K8 quadratic
+  forms -> gradient: weights on the pattern of Q (Hutchinson probes via SDDMM, or the exact
+  Takahashi inverse) -> K11 adjoint of the assembly -> one dot product per parameter.
+
+``logLike`` keeps the reference signature and return convention (``-like/(nobs r)``, ``-g/(nobs r)``)
+and adds two keyword arguments: ``probes=`` (inject the +-1 probe matrix instead of drawing it from
+the global legacy RNG) and ``exact_grad=`` (Takahashi traces instead of the
+Hutchinson estimator).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+from scipy import sparse
+
+from ..engine import F64, Engine, to_dev
+
+
+class SPDE2D:
+    # ---- configured by the concrete classes in spdes/__init__.py
+    name = ""            # reference ``type`` prefix
+    timed = False
+    kvar = False         # spline kappa
+    Hkind = "iso"        # "iso" | "aniso" | "ha"
+    Hvar = False
+    wkind = None         # None | "const" | "var"
+    aflav = 1            # spde_combine_A flavour for A (0 spatial, 1 "sum", 2 "paren")
+    divide = False       # Q / (dt*sigma) instead of (1/(dt*sigma)) * Q
+    default_own = ()     # default own parameters (without mod0 block and tau)
+
+    def __init__(self, grid, mod0=None, par=None, bc=3) -> None:
+        self.grid = grid
+        self.type = "%s-bc%d" % (self.name, bc)
+        self.Q = None
+        self.Q_fac = None
+        self.data = None
+        self.r = None
+        self.S = None
+        self.bc = bc
+        self.mod0 = mod0
+        self.Np = grid.Nbs2
+        self.fitQ0 = True
+        self._state = None
+        self._obs = None
+        M, N = grid.shape[0], grid.shape[1]
+        self.engine = Engine.get(M, N, grid.T if self.timed else 1, bc)
+        if self.timed and mod0 is None:
+            raise ValueError("space-time models need an initial-field model mod0")
+        if bc == 2 and not self.Hvar:
+            raise ValueError("bc=2 with a constant diffusion tensor is undefined in the reference "
+                             "(AcH_2D_b2.cpp:105 returns NaN); use a var-* model")
+        if par is None:
+            self.setPars(self._default_par(joint=False))
+        else:
+            self.setQ(par=par)
+
+    # ------------------------------------------------------------------ parameters
+    def _default_own(self):
+        out = []
+        for v in self.default_own:
+            out.extend(v if isinstance(v, (list, tuple)) else [v])
+        return out
+
+    def _default_par(self, joint: bool):
+        own = self._default_own()
+        if joint and self.timed:
+            return np.hstack([own, self.mod0.getPars()[:-1], np.log(100)]).astype("float64")
+        return np.hstack([own, np.log(100)]).astype("float64")
+
+    @property
+    def n_own(self) -> int:
+        nk = self.Np if self.kvar else 1
+        nh = {"iso": 1, "aniso": 3, "ha": 3}[self.Hkind] * (self.Np if self.Hvar else 1)
+        nw = 0 if self.wkind is None else (2 if self.wkind == "const" else 2 * self.Np)
+        return nk + nh + nw + (1 if self.timed else 0)
+
+    def _split(self, par):
+        nk = self.Np if self.kvar else 1
+        nh = self.Np if self.Hvar else 1
+        o = 0
+        p = {"kappa": par[o:o + nk]}
+        o += nk
+        p["gamma"] = par[o:o + nh]
+        o += nh
+        if self.Hkind != "iso":
+            p["vx"], p["vy"] = par[o:o + nh], par[o + nh:o + 2 * nh]
+            o += 2 * nh
+        if self.wkind == "const":
+            p["w"] = par[o:o + 2]
+            o += 2
+        elif self.wkind == "var":
+            p["w"] = par[o:o + 2 * self.Np]
+            o += 2 * self.Np
+        if self.timed:
+            p["sigma"] = par[o]
+            o += 1
+        return p
+
+    def getPars(self, onlySelf=True) -> np.ndarray:
+        if onlySelf or not self.timed:
+            return np.hstack([self._own, self.tau]).astype("float64")
+        return np.hstack([self._own, self.mod0.getPars()[:-1], self.tau]).astype("float64")
+
+    def setPars(self, par) -> None:
+        par = np.array(par, dtype="float64")
+        self._own = par[:self.n_own].copy()
+        p = self._split(par)
+        sc = (lambda v: v if v.size > 1 else float(v[0]))
+        self.kappa, self.gamma = sc(p["kappa"]), sc(p["gamma"])
+        if "vx" in p:
+            self.vx, self.vy = sc(p["vx"]), sc(p["vy"])
+        if self.wkind == "const":
+            self.wx, self.wy = float(p["w"][0]), float(p["w"][1])
+        elif self.wkind == "var":
+            self.wx, self.wy = p["w"][:self.Np], p["w"][self.Np:]
+        if self.timed:
+            self.sigma = float(p["sigma"])
+            if par.size > self.n_own + 1:
+                self.mod0.setPars(par[self.n_own:])
+        self.tau = par[-1]
+        if not self.timed:
+            self.sigma = np.log(np.sqrt(1 / np.exp(self.tau)))
+
+    def initFit(self, data, **kwargs):
+        data = np.asarray(data, dtype="float64")
+        assert data.shape[0] <= self.grid.n
+        if kwargs.get("fitQ0") is not None:
+            assert type(kwargs.get("fitQ0")) is bool
+            self.fitQ0 = kwargs.get("fitQ0")
+        par = self._default_par(joint=self.fitQ0)
+        self.data = data
+        self.r = data.shape[1] if data.ndim == 2 else 1
+        idx = kwargs.get("idx")
+        self.S = self.grid.getS(idxs=idx)
+        self._set_obs(self.grid.obs_nodes(idx))
+        return par
+
+    def _set_obs(self, nodes):
+        nodes = np.asarray(nodes, dtype=np.int64)
+        cnt = np.bincount(nodes, minlength=self.engine.n).astype(np.float64)
+        self._obs = {"nodes": to_dev(nodes, torch.int64), "cnt": to_dev(cnt), "nobs": int(nodes.size)}
+
+    def setQ(self, par=None, S=None):
+        if par is None:
+            par = self.getPars()
+        else:
+            self.setPars(par)
+        if S is not None:
+            self.S = S
+        self.Q, self.Q_fac, _ = self.makeQ(par=np.asarray(par, dtype="float64"), grad=False)
+        self.S = self.grid.getS()
+        self._set_obs(self.grid.obs_nodes())
+
+    def print(self, par):
+        p = self._split(np.asarray(par, dtype="float64"))
+        s = "| κ = %2.2f" % np.exp(p["kappa"]).mean() + ", γ = %2.2f" % np.exp(p["gamma"]).mean()
+        if "vx" in p:
+            s += ", vx = %2.2f" % np.mean(p["vx"]) + ", vy = %2.2f" % np.mean(p["vy"])
+        if self.wkind is not None:
+            h = p["w"].size // 2
+            s += ", wx = %2.2f" % np.mean(p["w"][:h]) + ", wy = %2.2f" % np.mean(p["w"][h:])
+        if self.timed:
+            s += ", σ = %2.2f" % np.exp(p["sigma"])
+        s += ", τ = %2.2f" % np.exp(par[-1])
+        if self.timed and par.size > self.n_own + 1:
+            s += "\n Q0: " + self.mod0.print(par[self.n_own:])[:-10]
+        return s
+
+    # ------------------------------------------------------------------ fields (host NumPy, like the reference)
+    def _H_and_dirs(self, p, want_dirs):
+        """Diffusion tensor and, per diffusion parameter in the reference's order, dH/dtheta_i
+        (``advection_diffusion2D.py:100,131-155``; half-angle ``whittle_matern_ha2D.py:73-106``;
+        spline fields ``var_advection_var_diffusion2D.py:91-99,131-160``)."""
+        g = self.grid
+        dirs = []
+        I2 = np.eye(2)
+        if not self.Hvar:
+            gam = np.exp(p["gamma"][0])
+            if self.Hkind == "iso":
+                H = gam * I2
+                dirs = [gam * I2]
+            elif self.Hkind == "aniso":
+                vv = np.array([p["vx"][0], p["vy"][0]])
+                H = gam * I2 + np.outer(vv, vv)
+                dirs = [gam * I2]
+                for e in (np.array([1.0, 0.0]), np.array([0.0, 1.0])):
+                    dirs.append(np.outer(e, vv) + np.outer(vv, e))
+            else:
+                vx, vy = p["vx"][0], p["vy"][0]
+                aV = np.sqrt(vx ** 2 + vy ** 2)
+                mV = np.array([[vx, vy], [vy, -vx]])
+                ch, sh = (np.exp(aV) + np.exp(-aV)) / 2, (np.exp(aV) - np.exp(-aV)) / 2
+                H = gam * (ch * I2 + sh / aV * mV)
+                dirs = [H,
+                        gam / aV * (vx * sh * I2 + vx / aV * (ch - sh / aV) * mV + sh * np.array([[1, 0], [0, -1]])),
+                        gam / aV * (vy * sh * I2 + vy / aV * (ch - sh / aV) * mV + sh * np.array([[0, 1], [1, 0]]))]
+            return H, dirs
+        gam = np.exp(g.evalBH(par=p["gamma"]))                      # (Ns, 4)
+        H = I2 * (np.stack([gam, gam], axis=2))[:, :, :, None]
+        if self.Hkind == "aniso":
+            vv = np.stack([g.evalBH(p["vx"]), g.evalBH(p["vy"])], axis=2)
+            H = H + vv[:, :, :, None] * vv[:, :, None, :]
+        elif self.Hkind == "ha":
+            raise NotImplementedError("spatially varying half-angle diffusion: next round (SURVEY.md section 8f)")
+        if want_dirs:
+            for i in range(self.Np):
+                dg = g.bsH[:, :, i] * gam
+                dirs.append(I2 * (np.stack([dg, dg], axis=2)[:, :, :, None]))
+            if self.Hkind == "aniso":
+                zero = np.zeros_like(gam)
+                for comp in (0, 1):
+                    for i in range(self.Np):
+                        b = g.bsH[:, :, i]
+                        dv = np.stack([b, zero], axis=2) if comp == 0 else np.stack([zero, b], axis=2)
+                        dirs.append(vv[:, :, :, None] * dv[:, :, None, :] + dv[:, :, :, None] * vv[:, :, None, :])
+        return H, dirs
+
+    # ------------------------------------------------------------------ assembly on the device
+    def _assemble(self, par, need_Q0_state=False):
+        """theta -> device state: kappa, A9, Q (slot layout) (+ mod0 state)."""
+        g, eng = self.grid, self.engine
+        par = np.asarray(par, dtype="float64")
+        p = self._split(par)
+        V = g.V
+        dt = g.dt if self.timed else 0.0
+        kap = np.exp(g.evalB(par=p["kappa"])) if self.kvar else np.exp(p["kappa"][:1])
+        H, _ = self._H_and_dirs(p, want_dirs=False)
+        st = {"par": par, "p": p, "V": V, "dt": dt, "kappa": to_dev(kap), "H": H}
+        ah = eng.ah_stencil(g.hx, g.hy, to_dev(H), self.Hvar)
+        aw = None
+        if self.wkind == "const":
+            st["ws"] = np.array(p["w"], dtype="float64")
+            aw = eng.aw_stencil(g.hx, g.hy, to_dev(st["ws"]), None, False, 3, False)
+        elif self.wkind == "var":
+            st["ws"] = np.ascontiguousarray(g.evalAdv(p["w"]))
+            aw = eng.aw_stencil(g.hx, g.hy, to_dev(st["ws"]), None, True, 3, True)
+        st["A9"] = eng.combine_A(self.aflav if self.timed else 0, V, dt, st["kappa"], ah, aw)
+        if not self.timed:
+            st["Q"] = eng.atda(st["A9"], st["kappa"], V, 0)
+            st["sigma"] = 1.0
+            return st
+        sigma = float(np.exp(p["sigma"]))
+        st["sigma"] = sigma
+        joint = par.size > self.n_own + 1
+        st["joint"] = joint
+        if joint:
+            st0 = self.mod0._assemble(par[self.n_own:])
+        else:
+            if self.mod0._state is None:
+                self.mod0.setQ()
+            st0 = self.mod0._state
+        st["mod0"] = st0
+        AtDA = eng.atda(st["A9"], st["kappa"], V, 1)
+        st["Q"] = eng.fill_spacetime(AtDA, st["A9"], st["kappa"], V, st0["Q"], sigma, dt, self.divide)
+        return st
+
+    def makeQ(self, par, grad=True):
+        """Returns ``(Q, Q_fac, dQ)`` like the reference.  ``Q`` is a SciPy CSC matrix exported from
+        the device, ``Q_fac`` a :class:`Factor` of it.  The reference materialises one n x n sparse
+        ``dQ_i`` per parameter (``advection_diffusion2D.py:119-182``); here the derivative enters
+        ``logLike`` through the adjoint of the assembly and is never formed, so ``dQ`` is a list of
+        callables ``dQ[i](X)`` evaluated by directional differencing of the assembly."""
+        st = self._assemble(np.asarray(par, dtype="float64"))
+        self._state = st
+        fac = self.engine.factorize(0, st["Q"])
+        Q = self.engine.to_scipy(st["Q"])
+        return Q, fac, ([] if grad else None)
+
+    # public stencil wrappers with the reference's return type (advection_diffusion2D.py:226-260)
+    def _stencil_to_csc(self, a9):
+        eng = self.engine
+        a9 = a9.cpu().numpy().reshape(9, eng.Ns)
+        k = np.arange(eng.Ns)
+        i, j = k % eng.M, k // eng.M
+        rows, cols, vals = [], [], []
+        for s in range(9):
+            ii, jj = i + (s % 3 - 1), j + (s // 3 - 1)
+            if self.bc == 2:
+                ii, jj = ii % eng.M, jj % eng.N
+                ok = np.ones(eng.Ns, bool)
+            else:
+                ok = (ii >= 0) & (ii < eng.M) & (jj >= 0) & (jj < eng.N)
+            rows.append(k[ok]); cols.append((jj * eng.M + ii)[ok]); vals.append(a9[s][ok])
+        return sparse.csc_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(eng.Ns, eng.Ns))
+
+    def Ah(self, Hs) -> sparse.csc_matrix:
+        Hs = np.array(Hs, dtype="float64")
+        return self._stencil_to_csc(self.engine.ah_stencil(self.grid.hx, self.grid.hy, to_dev(Hs), Hs.ndim == 4))
+
+    def Aw(self, ws, dws=None, diff=3) -> sparse.csc_matrix:
+        ws = np.array(ws, dtype="float64")
+        face = ws.ndim == 2
+        d = None if dws is None else to_dev(np.array(dws, dtype="float64"))
+        return self._stencil_to_csc(self.engine.aw_stencil(self.grid.hx, self.grid.hy, to_dev(ws), d, face, diff, face))
+
+    def setClib(self) -> None:      # the reference compiles / loads its C++ here; nothing to do
+        return None
+
+    # ------------------------------------------------------------------ gradient contraction (K11)
+    def _grad_from_weights(self, st, W):
+        """sum(W .* dQ_i) for every own parameter i (and the mod0 block when fitted jointly),
+        from the adjoint of the assembly; parameter order as ``advection_diffusion2D.py:119-182``."""
+        g, eng = self.grid, self.engine
+        Ns = eng.Ns
+        V, dt, sigma = st["V"], st["dt"], st["sigma"]
+        GA, Gq, GQ0 = eng.assembly_adjoint(W, st["A9"], st["kappa"], V, sigma, dt, self.timed)
+        out = []
+        # kappa
+        kap = st["kappa"]
+        GAc = GA[4 * Ns:5 * Ns]
+        if self.timed:
+            qs = ((V * kap) * (1.0 / V)) * (V * kap)
+            u = (V * dt) * kap * GAc + 2.0 * qs * Gq
+        else:
+            u = V * kap * GAc
+        if self.kvar:
+            out.extend(eng.gemv_t(self._bs_dev(), u.contiguous()).cpu().numpy().tolist())
+        else:
+            out.append(Engine.dot(u.contiguous(), torch.ones_like(u)))
+        # diffusion
+        _, dirs = self._H_and_dirs(st["p"], want_dirs=True)
+        sgn = -dt if self.timed else -1.0
+        for dH in dirs:
+            ah = eng.ah_stencil(g.hx, g.hy, to_dev(dH), self.Hvar)
+            out.append(sgn * Engine.dot(GA, ah))
+        # advection
+        if self.wkind == "const":
+            wsd = to_dev(st["ws"])
+            for d in (1, 2):
+                out.append(dt * Engine.dot(GA, eng.aw_stencil(g.hx, g.hy, wsd, None, False, d, False)))
+        elif self.wkind == "var":
+            wsd = to_dev(st["ws"])
+            for i in range(2 * self.Np):
+                dpar = np.zeros(2 * self.Np)
+                dpar[i] = 1
+                dws = to_dev(np.ascontiguousarray(g.evalAdv(dpar)))
+                aw = eng.aw_stencil(g.hx, g.hy, wsd, dws, True, 1 if i < self.Np else 2, True)
+                out.append(dt * Engine.dot(GA, aw))
+        if self.timed:
+            # log sigma: dQ = -(Q - blockdiag(Q0-part))   (advection_diffusion2D.py:170-175)
+            s_total = Engine.dot(W, st["Q"])
+            s_q0 = Engine.dot(GQ0, st["mod0"]["Q"])
+            out.append(-(s_total - s_q0))
+            if st["joint"]:
+                out.extend(self.mod0._grad_from_weights(st["mod0"], GQ0))
+        return out
+
+    def _bs_dev(self):
+        if getattr(self, "_bs_cache", None) is None:
+            self._bs_cache = to_dev(np.ascontiguousarray(self.grid.bs))
+        return self._bs_cache
+
+    # ------------------------------------------------------------------ likelihood (advection_diffusion2D.py:187-223)
+    def logLike(self, par, nh1=100, grad=True, probes=None, exact_grad=False):
+        eng = self.engine
+        par = np.asarray(par, dtype="float64")
+        if self._obs is None or self.data is None:
+            raise RuntimeError("call initFit(data, idx=...) first")
+        r, nobs = self.r, self._obs["nobs"]
+        obs, cnt = self._obs["nodes"], self._obs["cnt"]
+        data = to_dev(self.data.reshape(nobs, r))
+        tau = float(np.exp(par[-1]))
+        st = self._assemble(par)
+        self._state = st
+        Q = st["Q"]
+        eng.factorize(0, Q)
+        ldQ = eng.logdet(0)
+        eng.factorize(1, Q, cnt, tau)
+        ldQc = eng.logdet(1)
+        mu_c = eng.solve(1, eng.scatter_obs(data, obs, tau))          # Q_c^-1 S^T data tau
+        quad = Engine.dot(mu_c, eng.q_apply(Q, mu_c))
+        resid = Engine.residual_ss(data, mu_c, obs)
+        like = 1 / 2 * ldQ * r + nobs * r * np.log(tau) / 2 - 1 / 2 * ldQc * r - 1 / 2 * quad - tau / 2 * resid
+        self.last = {"mu_c": mu_c, "logdetQ": ldQ, "logdetQc": ldQc, "quad": quad, "resid": resid}
+        if not grad:
+            return -like / (nobs * r)
+        if exact_grad:
+            Z = eng.selinv(0)
+            Zc = eng.selinv(1)
+            nd = eng.nslots // 2
+            tr_tau = Engine.dot(cnt, Zc[nd * eng.n:(nd + 1) * eng.n].contiguous()) * tau
+            W = (Z - Zc) * (0.5 * r)
+            del Z, Zc
+        else:
+            if probes is None:
+                probes = (2 * np.random.randint(1, 3, self.grid.n * nh1) - 3).reshape(self.grid.n, nh1)
+            Vp = to_dev(np.asarray(probes, dtype=np.float64))
+            nh1 = Vp.shape[1]
+            TrQ = eng.solve(0, Vp.clone())
+            TrQc = eng.solve(1, Vp.clone())
+            a = 0.5 * r / nh1
+            W = eng.sddmm(TrQ, Vp, a)
+            W = eng.sddmm(TrQc, Vp, -a, W)
+            tr_tau = Engine.wdot(TrQc, Vp, cnt) * tau / nh1
+        W = eng.sddmm(mu_c, mu_c, -0.5, W)
+        g_par = np.zeros(par.size)
+        gi = self._grad_from_weights(st, W)
+        g_par[:len(gi)] = gi
+        g_par[-1] = nobs * r / 2 - 1 / 2 * tr_tau * r - tau / 2 * resid
+        return -like / (nobs * r), -g_par / (nobs * r)

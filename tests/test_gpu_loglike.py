@@ -1,0 +1,129 @@
+"""GPU parity of the numeric hot path: factorisation / logdet / solves / samples / selected inverse /
+log-likelihood and gradient, against the reference's golden outputs and the CPU oracle.
+Tolerances (BASELINE.json north_star): 1e-9 relative in FP64."""
+import numpy as np
+import pytest
+import torch
+from scipy import sparse
+
+import spde_oracle as so
+from helpers import golden_names, load_golden, make_grids, make_oracle, relerr
+
+pytestmark = pytest.mark.gpu
+
+
+def _build(d):
+    import spdepy_b200 as sp
+    g, g0 = make_grids(d)
+    kw = {}
+    if g0 is not None:
+        kw["mod0"] = sp.model(grid=g0, spde=d["mod0_spde"], ha=d["ha"], anisotropic=d["ani"], bc=d["bc"], parameters=d["mod0_par"])
+    return sp.model(grid=g, spde=d["spde"], ha=d["ha"], anisotropic=d["ani"], bc=d["bc"], **kw)
+
+
+def _dense(Q):
+    A = sparse.tril(Q).toarray()
+    return A + np.tril(A, -1).T
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_factor_methods(name):
+    d = load_golden(name)
+    mod = _build(d)
+    mod.mod.setQ(d["par"])
+    fac = mod.mod.Q_fac
+    A = _dense(d["Q"])
+    n = A.shape[0]
+    perm = fac.P().astype(np.int64)
+    L = np.linalg.cholesky(A[np.ix_(perm, perm)])
+    assert abs(fac.logdet() - 2 * np.log(np.diag(L)).sum()) <= 1e-9 * abs(fac.logdet())
+    assert abs(fac.logdet() - float(d["logdetQ"])) <= 1e-9 * abs(float(d["logdetQ"]))
+    rng = np.random.default_rng(0)
+    B = rng.normal(size=(n, 5))
+    assert relerr(fac.solve_A(B), np.linalg.solve(A, B)) < 1e-9
+    assert relerr(fac.solve_A(B[:, 0]), np.linalg.solve(A, B[:, 0])) < 1e-9
+    x = fac.apply_Pt(fac.solve_Lt(B, use_LDLt_decomposition=False))
+    ref = np.empty_like(B)
+    ref[perm] = np.linalg.solve(L.T, B)
+    assert relerr(x, ref) < 1e-9
+    assert relerr(fac.solve_L(fac.apply_P(B)), np.linalg.solve(L, B[perm])) < 1e-9
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_sample_update_against_oracle(name):
+    """Model.sample / Model.update with identical normal draws and the build's permutation."""
+    d = load_golden(name)
+    mod = _build(d)
+    mod.mod.setQ(d["par"])
+    mod.setModel()
+    X = mod.sample(n=4, seed=3, simple=True)
+    perm = mod.Q_fac.P().astype(np.int64)
+    so.set_factor(None, lambda n: perm)
+    try:
+        Xo = so.sample(d["Q"], mod.grid.getS(), n=4, seed=3)
+    finally:
+        so.set_factor(None, None)
+    assert relerr(X, Xo) < 1e-9
+    mod.update(y=d["data"][:, 0], idx=d["idx"])
+    assert relerr(mod.mu, d["upd_mu"]) < 1e-9
+    assert relerr(mod.getQ().diagonal(), d["upd_Qdiag"]) < 1e-13
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_selected_inverse(name):
+    d = load_golden(name)
+    mod = _build(d)
+    mod.mod.setQ(d["par"])
+    eng = mod.mod.engine
+    Z = eng.selinv(0).cpu().numpy()
+    Zd = np.linalg.inv(_dense(d["Q"]))
+    full = eng.pattern.to_csc(Z).toarray()
+    mask = eng.pattern.to_csc(np.ones_like(Z)).toarray() != 0
+    assert np.abs(full[mask] - Zd[mask]).max() <= 1e-9 * np.abs(Zd).max()
+    mod.setModel()
+    assert relerr(mod.qinv(simple=False), np.diag(Zd)) < 1e-9
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_loglike_and_hutchinson_gradient_vs_reference(name):
+    """like and jac with the reference's own probe draw (np.random.seed(4)) against the values the
+    unmodified reference returned."""
+    d = load_golden(name)
+    mod = _build(d)
+    m = mod.mod
+    m.initFit(d["data"], idx=d["idx"], fitQ0=d["fitQ0"])
+    like, jac = m.logLike(d["par"], grad=True, probes=d["probes"].astype(np.float64))
+    assert abs(like - d["like"]) <= 1e-9 * abs(d["like"])
+    assert relerr(m.last["mu_c"].cpu().numpy(), d["mu_c"].reshape(-1, 2)) < 1e-9
+    assert abs(m.last["logdetQ"] - float(d["logdetQ"])) <= 1e-9 * abs(float(d["logdetQ"]))
+    assert abs(m.last["logdetQc"] - float(d["logdetQc"])) <= 1e-9 * abs(float(d["logdetQc"]))
+    assert np.abs(jac - d["jac"]).max() <= 1e-9 * np.abs(d["jac"]).max(), (jac, d["jac"])
+    assert m.logLike(d["par"], grad=False) == pytest.approx(like, rel=1e-12)
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_exact_gradient_vs_oracle_dense_inverse(name):
+    """Takahashi gradient against the oracle's formula evaluated with dense inverses."""
+    d = load_golden(name)
+    mod = _build(d)
+    m = mod.mod
+    m.initFit(d["data"], idx=d["idx"], fitQ0=d["fitQ0"])
+    like, jac = m.logLike(d["par"], grad=True, exact_grad=True)
+    orc = make_oracle(d)
+    orc.initFit(d["data"], idx=d["idx"])
+    like_o, jac_o = orc.logLike_exact(d["par"])
+    assert abs(like - like_o) <= 1e-9 * abs(like_o)
+    assert np.abs(jac - jac_o).max() <= 1e-9 * np.abs(jac_o).max(), (jac, jac_o)
+
+
+def test_not_positive_definite_raises():
+    import spdepy_b200 as sp
+    from spdepy_b200._lib import NotPositiveDefiniteError
+    d = load_golden("wm_iso_bc3")
+    mod = _build(d)
+    mod.mod.setQ(d["par"])
+    eng = mod.mod.engine
+    Q = mod.mod._state["Q"].clone()
+    Q[(eng.nslots // 2) * eng.n + 3] = -1.0
+    with pytest.raises(NotPositiveDefiniteError):
+        eng.factorize(0, Q)
