@@ -111,6 +111,12 @@ int spde_plan_supernodes(const spde_plan *p, int32_t *h_first /* nsuper+1 */, in
  * Pass h_out=NULL to query the count and element size.  Test / inspection interface. */
 int spde_plan_export(spde_plan *p, int prog, int k, int what, void *h_out, int64_t *count, int *elem_size);
 
+/* Per-launch device timing of the schedules (CUDA events around every launch; serialises the stream,
+ * so never on inside a timed benchmark region).  h_out (may be NULL): 8x16 accumulated milliseconds
+ * indexed [launch kind][GEMM variant] followed by 8x16 launch counts.  Kinds: 0 GEMM, 1 POTRF,
+ * 2 extend-add, 3 memset, 4 gather, 5 W^T W, 6 extract.  GEMM variant = cfg*4 + a_kmaj*2 + b_kmaj. */
+int spde_plan_profile(spde_plan *p, int enable, double *h_out, int reset);
+
 /* ------------------------------------------------------------------ numeric factorisation (K4,K5,K6) */
 
 /* L L^T = P (Q + tau*diag(d_cnt)) P^T.  d_Q in Q25/Q43 layout (only the lower-triangle slots of

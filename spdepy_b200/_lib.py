@@ -49,6 +49,7 @@ _SIGS = {
     "spde_plan_perm": (c_int, [c_vp, c_vp]),
     "spde_plan_supernodes": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp]),
     "spde_plan_export": (c_int, [c_vp, c_int, c_int, c_int, c_vp, ctypes.POINTER(c_i64), ctypes.POINTER(c_int)]),
+    "spde_plan_profile": (c_int, [c_vp, c_int, c_vp, c_int]),
     "spde_factorize": (c_int, [c_vp, c_int, c_vp, c_vp, c_dbl, c_vp]),
     "spde_factor_info": (c_int, [c_vp, c_int, ctypes.POINTER(c_int), ctypes.POINTER(c_int)]),
     "spde_logdet": (c_int, [c_vp, c_int, ctypes.POINTER(c_dbl), c_vp]),
@@ -145,6 +146,12 @@ class PlanHandle:
         if cnt.value:
             check(lib.spde_plan_export(self.h, prog, k, what, out.ctypes.data, None, None))
         return out
+
+    def profile(self, enable: bool, reset: bool = True):
+        """Toggle per-launch timing; returns (ms, counts) arrays [kind, variant] accumulated so far."""
+        out = np.zeros(2 * 8 * 16)
+        check(lib.spde_plan_profile(self.h, int(enable), out.ctypes.data, int(reset)))
+        return out[:128].reshape(8, 16), out[128:].reshape(8, 16)
 
     def stats(self) -> dict:
         return {"n": self.n, "nsuper": self.info(1), "nnzL": self.info(2), "flops": self.info_d(3),

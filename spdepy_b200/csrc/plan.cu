@@ -302,6 +302,13 @@ static int run_program(Plan &p, Program &P, int which, cudaStream_t st, double *
     int rc = upload_program(P);
     if (rc) return rc;
     GemmSpaces sp = spaces_of(p, which);
+    std::vector<cudaEvent_t> ev;
+    if (p.prof_on) {
+        ev.resize(P.launches.size() + 1);
+        for (auto &e : ev) cudaEventCreate(&e);
+        cudaEventRecord(ev[0], st);
+    }
+    size_t li = 0;
     for (const Launch &L : P.launches) {
         switch (L.kind) {
         case LK_GEMM:
@@ -329,6 +336,19 @@ static int run_program(Plan &p, Program &P, int which, cudaStream_t st, double *
         }
         }
         SPDE_LAUNCH_CHECK();
+        if (p.prof_on) cudaEventRecord(ev[++li], st);
+    }
+    if (p.prof_on) {
+        SPDE_CUDA_CHECK(cudaStreamSynchronize(st));
+        for (size_t i = 0; i < P.launches.size(); i++) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
+            const Launch &L = P.launches[i];
+            const int v = L.kind == LK_GEMM ? L.variant : 0;
+            p.prof_ms[L.kind][v] += ms;
+            p.prof_cnt[L.kind][v] += 1;
+        }
+        for (auto &e : ev) cudaEventDestroy(e);
     }
     return SPDE_OK;
 }
@@ -479,6 +499,18 @@ extern "C" int spde_plan_export(spde_plan *pp, int prog, int k, int what, void *
     if (count) *count = cnt;
     if (elem_size) *elem_size = es;
     if (h_out && cnt) memcpy(h_out, src, (size_t)cnt * es);
+    return SPDE_OK;
+}
+
+extern "C" int spde_plan_profile(spde_plan *pp, int enable, double *h_out /* 8*16*2 or NULL */, int reset)
+{
+    Plan &p = *reinterpret_cast<Plan *>(pp);
+    if (h_out) {
+        memcpy(h_out, p.prof_ms, sizeof p.prof_ms);
+        memcpy(h_out + 8 * 16, p.prof_cnt, sizeof p.prof_cnt);
+    }
+    if (reset) { memset(p.prof_ms, 0, sizeof p.prof_ms); memset(p.prof_cnt, 0, sizeof p.prof_cnt); }
+    p.prof_on = enable != 0;
     return SPDE_OK;
 }
 

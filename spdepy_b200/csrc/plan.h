@@ -96,6 +96,10 @@ struct Plan {
     ZEntry *d_zentries = nullptr;
     int status[2] = {0, 0}, bad_col[2] = {-1, -1};
     bool factored[2] = {false, false};
+    // optional per-launch timing (CUDA events), accumulated per (launch kind, GEMM variant)
+    bool prof_on = false;
+    double prof_ms[8][16] = {{0}};
+    double prof_cnt[8][16] = {{0}};
 
     void build_layout();
     void build_factor_program();

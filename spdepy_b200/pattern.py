@@ -55,7 +55,9 @@ class Pattern:
 
     def to_csc(self, flat: np.ndarray) -> sparse.csc_matrix:
         """slot-major values -> canonical CSC on the full geometric pattern (explicit zeros kept)"""
-        return sparse.csc_matrix((np.asarray(flat)[self.gather], self.indices, self.indptr), shape=(self.n, self.n))
+        # indices/indptr are copied: SciPy shares them otherwise and eliminate_zeros() edits in place
+        return sparse.csc_matrix((np.asarray(flat)[self.gather], self.indices.copy(), self.indptr.copy()),
+                                 shape=(self.n, self.n))
 
     def from_sparse(self, Q) -> np.ndarray:
         """sparse matrix whose pattern is inside the mesh pattern -> slot-major values"""
