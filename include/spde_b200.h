@@ -48,6 +48,8 @@ typedef struct spde_plan spde_plan;
 
 int spde_abi_version(void);
 const char *spde_last_error(void);
+/* number of kernels this library has launched so far in this process (optionally reset) */
+long long spde_launch_count(int reset);
 
 /* ------------------------------------------------------------------ stencils (K2) */
 

@@ -122,8 +122,16 @@ def run_case(case):
     return name, Q.shape[0], Q.nnz, like
 
 
+def copy_fitted_theta():
+    """The 92 fitted parameters of the SINMOD application (SURVEY.md section 8d, C3 inputs): a data fixture of
+    the reference (``examples/sinmod_example/fits/var_advection_var_diffusion_ani_bc1.npy``)."""
+    p = np.load(os.path.join(rh.REF_ROOT, "examples", "sinmod_example", "fits", "var_advection_var_diffusion_ani_bc1.npy"))
+    np.save(os.path.join(OUT, "c3_theta.npy"), p)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
+    copy_fitted_theta()
     only = set(sys.argv[1:])
     for c in CASES:
         if only and c[0] not in only:

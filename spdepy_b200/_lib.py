@@ -37,6 +37,7 @@ c_int, c_dbl, c_vp, c_i64 = ctypes.c_int, ctypes.c_double, ctypes.c_void_p, ctyp
 _SIGS = {
     "spde_abi_version": (c_int, []),
     "spde_last_error": (ctypes.c_char_p, []),
+    "spde_launch_count": (ctypes.c_longlong, [c_int]),
     "spde_ah_stencil": (c_int, [c_int, c_int, c_int, c_dbl, c_dbl, c_vp, c_int, c_vp, c_vp]),
     "spde_aw_stencil": (c_int, [c_int, c_int, c_int, c_dbl, c_dbl, c_vp, c_vp, c_int, c_int, c_int, c_vp, c_vp]),
     "spde_combine_A": (c_int, [c_int, c_int, c_dbl, c_dbl, c_vp, c_int, c_vp, c_vp, c_vp, c_vp]),

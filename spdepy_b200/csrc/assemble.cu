@@ -354,6 +354,7 @@ extern "C" int spde_ah_stencil(int M, int N, int bc, double hx, double hy, const
     Geo g{M, N, 1, bc};
     k_ah_stencil<<<cdiv(M * N, 128), 128, 0, (cudaStream_t)stream>>>(g, hx, hy, d_H, face, d_ah9);
     SPDE_LAUNCH_CHECK();
+    count_launch();
     return SPDE_OK;
 }
 
@@ -364,6 +365,7 @@ extern "C" int spde_aw_stencil(int M, int N, int bc, double hx, double hy, const
     Geo g{M, N, 1, bc};
     k_aw_stencil<<<cdiv(M * N, 128), 128, 0, (cudaStream_t)stream>>>(g, hx, hy, d_G, d_dG, face, diff, nan_to_zero, d_aw9);
     SPDE_LAUNCH_CHECK();
+    count_launch();
     return SPDE_OK;
 }
 
@@ -373,6 +375,7 @@ extern "C" int spde_combine_A(int Ns, int flavour, double V, double dt, const do
     if (flavour < 0 || flavour > 5) { set_error("spde_combine_A: bad flavour"); return SPDE_ERR_ARG; }
     k_combine_A<<<cdiv(Ns, 128), 128, 0, (cudaStream_t)stream>>>(Ns, flavour, V, dt, d_kappa, kvar, d_ah9, d_aw9, d_A9);
     SPDE_LAUNCH_CHECK();
+    count_launch();
     return SPDE_OK;
 }
 
@@ -383,6 +386,7 @@ extern "C" int spde_atda(int M, int N, int bc, const double *d_A9, const double 
     Geo g{M, N, 1, bc};
     k_atda<<<cdiv(M * N, 128), 128, 0, (cudaStream_t)stream>>>(g, d_A9, d_kappa, kvar, V, mode, d_out25);
     SPDE_LAUNCH_CHECK();
+    count_launch();
     return SPDE_OK;
 }
 
@@ -396,5 +400,6 @@ extern "C" int spde_fill_spacetime(int M, int N, int T, int bc, const double *d_
     k_fill_spacetime<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(g, d_AtDA25, d_A9, d_kappa, kvar, V, d_Q0_25,
                                                                     sigma, dt, divide, d_Q43);
     SPDE_LAUNCH_CHECK();
+    count_launch();
     return SPDE_OK;
 }

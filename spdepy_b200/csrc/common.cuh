@@ -10,6 +10,7 @@
 namespace spde {
 
 void set_error(const std::string &msg);
+void count_launch(int n = 1);   // bookkeeping for spde_launch_count (bench.py's gpu_launches)
 
 #define SPDE_CUDA_CHECK(expr)                                                              \
     do {                                                                                   \

@@ -10,6 +10,8 @@ namespace spde {
 
 static thread_local std::string g_err;
 void set_error(const std::string &msg) { g_err = msg; }
+static long long g_launches = 0;
+void count_launch(int n) { g_launches += n; }
 
 // ---------------------------------------------------------------------------------------------
 // K4: Q (slot layout, original ordering) -> zeroed L store (permuted supernodal panels);
@@ -336,6 +338,7 @@ static int run_program(Plan &p, Program &P, int which, cudaStream_t st, double *
         }
         }
         SPDE_LAUNCH_CHECK();
+        if (L.kind != LK_ZERO) count_launch();
         if (p.prof_on) cudaEventRecord(ev[++li], st);
     }
     if (p.prof_on) {
@@ -382,6 +385,12 @@ using namespace spde;
 
 extern "C" int spde_abi_version(void) { return 1; }
 extern "C" const char *spde_last_error(void) { return g_err.c_str(); }
+extern "C" long long spde_launch_count(int reset)
+{
+    const long long v = g_launches;
+    if (reset) g_launches = 0;
+    return v;
+}
 
 extern "C" int spde_plan_create(int M, int N, int T, int bc, int max_rhs, spde_plan **out)
 {
@@ -525,6 +534,7 @@ extern "C" int spde_factorize(spde_plan *pp, int which, const double *d_Q, const
     SPDE_CUDA_CHECK(cudaMemsetAsync(p.d_L[which], 0, (size_t)p.l_size * sizeof(double), st));
     SPDE_CUDA_CHECK(cudaMemsetAsync(p.d_status, 0, sizeof(int), st));
     const int ncand = (int)p.cand_slots.size();
+    count_launch();
     k_scatter_q<<<148 * 8, 256, 0, st>>>(d_Q, p.d_qdest, p.d_cand, ncand, n, p.sym.nslots / 2, d_cnt, tau, p.d_L[which]);
     SPDE_LAUNCH_CHECK();
     rc = run_program(p, p.factor, which, st, nullptr);
@@ -553,6 +563,7 @@ extern "C" int spde_logdet(spde_plan *pp, int which, double *h_logdet, void *str
     if (!p.factored[which]) { set_error("spde_logdet: not factorised"); return SPDE_ERR_ARG; }
     cudaStream_t st = (cudaStream_t)stream;
     const int nb = 1024;
+    count_launch(2);
     k_logdet_partial<<<nb, 256, 0, st>>>(p.d_L[which], p.d_diagpos, p.sym.n, p.d_red);
     k_sum_final<<<1, 1024, 0, st>>>(p.d_red, nb, 2.0, p.d_red + nb);
     SPDE_LAUNCH_CHECK();
@@ -576,6 +587,7 @@ extern "C" int spde_solve(spde_plan *pp, int which, int mode, double *d_X, int k
         p.x_cap = need;
     }
     const int grid = 148 * 8;
+    count_launch(2);
     k_perm_in<<<grid, 256, 0, st>>>(d_X, p.d_perm, n, k, kp, (mode >> 2) & 1, p.d_X);
     SPDE_LAUNCH_CHECK();
     int rc;

@@ -260,6 +260,7 @@ extern "C" int spde_q_apply(int M, int N, int T, int bc, const double *d_Q, cons
     const long long total = (long long)M * N * T * k;
     k_q_apply<<<(int)std::min<long long>((total + 255) / 256, 148 * 32), 256, 0, (cudaStream_t)stream>>>(g, d_Q, d_X, k, d_Y);
     SPDE_LAUNCH_CHECK();
+    count_launch();
     return SPDE_OK;
 }
 
@@ -285,6 +286,7 @@ extern "C" int spde_sddmm(int M, int N, int T, int bc, const double *d_X, const 
     const long long blocks = std::min<long long>((n * 32 + 255) / 256, 148 * 16);
     k_sddmm<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(g, d_X, d_Y, k, alpha, accumulate, d_W);
     SPDE_LAUNCH_CHECK();
+    count_launch();
     return SPDE_OK;
 }
 
@@ -308,6 +310,7 @@ extern "C" int spde_assembly_adjoint(int M, int N, int T, int bc, const double *
         k_adj_cell<<<cdiv(Ns, 128), 128, 0, st>>>(g, 0, d_W, nullptr, nullptr, nullptr, d_A9, d_kappa, kvar, V, 1.0, d_GA9, d_Gq);
     }
     SPDE_LAUNCH_CHECK();
+    count_launch();
     return SPDE_OK;
 }
 
@@ -321,6 +324,7 @@ extern "C" int spde_gemv_t(const double *d_B, const double *d_u, int rows, int c
     k_gemv_t<<<dim3(nb, cols), 256, 0, st>>>(d_B, d_u, rows, cols, g_scratch);
     k_gemv_final<<<cols, 64, 0, st>>>(g_scratch, nb, d_out);
     SPDE_LAUNCH_CHECK();
+    count_launch();
     return SPDE_OK;
 }
 
@@ -360,6 +364,7 @@ extern "C" int spde_scatter_obs(const double *d_data, const int64_t *d_obs, int6
     k_scatter_obs<<<(int)std::min<long long>((len + 255) / 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(
         d_data, (const long long *)d_obs, nobs, r, tau, d_b);
     SPDE_LAUNCH_CHECK();
+    count_launch();
     return SPDE_OK;
 }
 
@@ -367,5 +372,6 @@ extern "C" int spde_add_diag(double *d_Qdiag, const double *d_cnt, double tau, i
 {
     k_add_diag<<<(int)std::min<long long>((n + 255) / 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(d_Qdiag, d_cnt, tau, n);
     SPDE_LAUNCH_CHECK();
+    count_launch();
     return SPDE_OK;
 }

@@ -30,10 +30,23 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+# bytes moved across PCIe and library calls issued, for bench.py's h2d/d2h/launch accounting
+COUNTERS = {"h2d": 0, "d2h": 0, "calls": 0}
+
+
 def to_dev(a, dtype=F64) -> torch.Tensor:
     if isinstance(a, torch.Tensor):
-        return a.to(device=_dev(), dtype=dtype).contiguous()
-    return torch.as_tensor(np.ascontiguousarray(a), dtype=dtype, device=_dev())
+        if not a.is_cuda:
+            COUNTERS["h2d"] += a.numel() * a.element_size()
+        return a.to(device=_dev(), dtype=dtype, non_blocking=True).contiguous()
+    a = np.ascontiguousarray(a)
+    COUNTERS["h2d"] += a.nbytes
+    return torch.as_tensor(a, dtype=dtype, device=_dev())
+
+
+def to_host(t: torch.Tensor) -> np.ndarray:
+    COUNTERS["d2h"] += t.numel() * t.element_size()
+    return t.cpu().numpy()
 
 
 class Factor:
@@ -168,6 +181,7 @@ class Engine:
     def logdet(self, which: int) -> float:
         out = ctypes.c_double()
         check(lib.spde_logdet(self.plan.h, which, ctypes.byref(out), _stream()))
+        COUNTERS['d2h'] += 8
         return out.value
 
     def solve(self, which: int, X: torch.Tensor, mode: int = 15) -> torch.Tensor:
@@ -190,18 +204,21 @@ class Engine:
     def dot(X: torch.Tensor, Y: torch.Tensor) -> float:
         out = ctypes.c_double()
         check(lib.spde_dot(ptr(X), ptr(Y), X.numel(), ctypes.byref(out), _stream()))
+        COUNTERS["d2h"] += 8
         return out.value
 
     @staticmethod
     def wdot(X: torch.Tensor, Y: torch.Tensor, w: torch.Tensor) -> float:
         out = ctypes.c_double()
         check(lib.spde_wdot(ptr(X), ptr(Y), ptr(w), X.shape[0], X.shape[1], ctypes.byref(out), _stream()))
+        COUNTERS["d2h"] += 8
         return out.value
 
     @staticmethod
     def residual_ss(data: torch.Tensor, mu: torch.Tensor, obs: torch.Tensor) -> float:
         out = ctypes.c_double()
         check(lib.spde_residual_ss(ptr(data), ptr(mu), ptr(obs), data.shape[0], data.shape[1], ctypes.byref(out), _stream()))
+        COUNTERS["d2h"] += 8
         return out.value
 
     def scatter_obs(self, data: torch.Tensor, obs: torch.Tensor, tau: float) -> torch.Tensor:
@@ -244,6 +261,6 @@ class Engine:
     def to_scipy(self, Q: torch.Tensor):
         """slot layout -> canonical SciPy CSC (what the reference exposes as ``mod.Q``); exact zeros
         are dropped, as SciPy's SpGEMM / sparse add do in the reference."""
-        m = self.pattern.to_csc(Q.cpu().numpy())
+        m = self.pattern.to_csc(to_host(Q))
         m.eliminate_zeros()
         return m

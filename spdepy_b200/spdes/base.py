@@ -21,7 +21,7 @@ import numpy as np
 import torch
 from scipy import sparse
 
-from ..engine import F64, Engine, to_dev
+from ..engine import F64, Engine, to_dev, to_host
 
 
 class SPDE2D:
@@ -322,7 +322,7 @@ class SPDE2D:
         else:
             u = V * kap * GAc
         if self.kvar:
-            out.extend(eng.gemv_t(self._bs_dev(), u.contiguous()).cpu().numpy().tolist())
+            out.extend(to_host(eng.gemv_t(self._bs_dev(), u.contiguous())).tolist())
         else:
             out.append(Engine.dot(u.contiguous(), torch.ones_like(u)))
         # diffusion
@@ -366,7 +366,9 @@ class SPDE2D:
             raise RuntimeError("call initFit(data, idx=...) first")
         r, nobs = self.r, self._obs["nobs"]
         obs, cnt = self._obs["nodes"], self._obs["cnt"]
-        data = to_dev(self.data.reshape(nobs, r))
+        data = self._obs.get("data")            # device-resident copy (bench.py's kernel-only arm)
+        if data is None:
+            data = to_dev(self.data.reshape(nobs, r))
         tau = float(np.exp(par[-1]))
         st = self._assemble(par)
         self._state = st
