@@ -210,7 +210,9 @@ k_gemm_grouped(const GemmTask *__restrict__ tasks, const TileRef *__restrict__ t
                 else *p += v;
                 if (mirror) {
                     double *q = gC - tk.c + tk.c2 + c + (long long)r * tk.ldc;
-                    if (beta0) *q = v; else *q += v;
+                    if (atomic) atomicAdd(q, v);
+                    else if (beta0) *q = v;
+                    else *q += v;
                 }
             }
         }

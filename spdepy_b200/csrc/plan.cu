@@ -2,9 +2,12 @@
 // extend-add, gathers, reductions), the program executor and the C ABI for plan / factor / solve
 // / selected inverse.
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "plan.h"
+
+extern "C" long long spde_launch_count(int reset);
 
 namespace spde {
 
@@ -97,16 +100,22 @@ __global__ void __launch_bounds__(256) k_potrf(const PotrfTask *__restrict__ tas
         }
         __syncthreads();
     }
-    // W = L^-1 by forward substitution on the identity, one column per thread; column c of W is
-    // kept in row c of the (free) upper triangle, so reads of thread c stay in its own row.
-    if (tid < b) {
-        const int c = tid;
-        const double wcc = 1.0 / a[c][c];
-        wd[c] = wcc;
-        for (int i = c + 1; i < b; i++) {
-            double s = -a[i][c] * wcc;
-            for (int k = c + 1; k < i; k++) s -= a[i][k] * a[c][k];
-            a[c][i] = s / a[i][i];
+    // W = L^-1 by forward substitution on the identity.  Column c of W is kept in row c of the (free)
+    // upper triangle; four lanes share a column and split the dot product over k, so the dependent
+    // chain per row is ~(i-c)/4 FMAs plus two shuffles instead of i-c.
+    {
+        const int c = tid >> 2, l = tid & 3;
+        const bool live = c < b;
+        const double wcc = live ? 1.0 / a[c][c] : 0.0;
+        if (live && l == 0) wd[c] = wcc;
+        for (int i = 1; i < NB; i++) {
+            double s = 0.0;
+            if (live && i > c && i < b)
+                for (int k = c + 1 + l; k < i; k += 4) s += a[i][k] * a[c][k];
+            s += __shfl_xor_sync(0xffffffffu, s, 1);
+            s += __shfl_xor_sync(0xffffffffu, s, 2);
+            if (live && l == 0 && i > c && i < b) a[c][i] = (-a[i][c] * wcc - s) / a[i][i];
+            __syncwarp();
         }
     }
     __syncthreads();
@@ -280,6 +289,7 @@ static int upload_program(Program &P)
 
 static void free_program(Program &P)
 {
+    for (int w = 0; w < 2; w++) if (P.graph[w]) { cudaGraphExecDestroy(P.graph[w]); P.graph[w] = nullptr; }
     cudaFree(P.d_gemm); cudaFree(P.d_tiles); cudaFree(P.d_potrf); cudaFree(P.d_ext); cudaFree(P.d_gather); cudaFree(P.d_wtw);
     P.uploaded = false;
 }
@@ -299,7 +309,7 @@ static GemmSpaces spaces_of(Plan &p, int which)
     return sp;
 }
 
-static int run_program(Plan &p, Program &P, int which, cudaStream_t st, double *d_Zq)
+static int issue_program(Plan &p, Program &P, int which, cudaStream_t st, double *d_Zq)
 {
     int rc = upload_program(P);
     if (rc) return rc;
@@ -356,8 +366,71 @@ static int run_program(Plan &p, Program &P, int which, cudaStream_t st, double *
     return SPDE_OK;
 }
 
+static void init_gemm_attributes()
+{
+    static bool done = false;
+    if (done) return;
+    done = true;
+#define A(BM, BN, WM, WN)                                                                                          \
+    cudaFuncSetAttribute(k_gemm_grouped<BM, BN, WM, WN, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes<BM, BN>()); \
+    cudaFuncSetAttribute(k_gemm_grouped<BM, BN, WM, WN, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes<BM, BN>());  \
+    cudaFuncSetAttribute(k_gemm_grouped<BM, BN, WM, WN, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes<BM, BN>());  \
+    cudaFuncSetAttribute(k_gemm_grouped<BM, BN, WM, WN, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes<BM, BN>());
+    A(128, 128, 2, 4) A(128, 64, 4, 2) A(64, 64, 2, 2)
+#undef A
+}
+
+// Run a schedule: first call plainly, second call captured into a CUDA graph, later calls replayed.  The
+// schedules are static per mesh (fixed task lists, fixed workspace pointers), so replay removes the host
+// cost of thousands of launches per evaluation.
+static int run_program(Plan &p, Program &P, int which, cudaStream_t st, double *d_Zq)
+{
+    if (p.prof_on || !p.use_graphs) return issue_program(p, P, which, st, d_Zq);
+    GemmSpaces sp = spaces_of(p, which);
+    unsigned long long key = 1469598103934665603ull;
+    for (int i = 0; i < 8; i++) key = (key ^ (unsigned long long)(uintptr_t)sp.base[i]) * 1099511628211ull;
+    key = (key ^ (unsigned long long)(uintptr_t)d_Zq) * 1099511628211ull;
+    if (P.graph[which] && P.graph_key[which] != key) {
+        cudaGraphExecDestroy(P.graph[which]);
+        P.graph[which] = nullptr;
+    }
+    if (!P.graph[which]) {
+        if (P.runs[which]++ == 0) return issue_program(p, P, which, st, d_Zq);   // warm run: uploads, lazy init
+        if (!p.cap_stream) {
+            SPDE_CUDA_CHECK(cudaStreamCreateWithFlags(&p.cap_stream, cudaStreamNonBlocking));
+            SPDE_CUDA_CHECK(cudaEventCreateWithFlags(&p.ev_in, cudaEventDisableTiming));
+            SPDE_CUDA_CHECK(cudaEventCreateWithFlags(&p.ev_out, cudaEventDisableTiming));
+        }
+        SPDE_CUDA_CHECK(cudaStreamBeginCapture(p.cap_stream, cudaStreamCaptureModeRelaxed));
+        const long long before = spde_launch_count(0);
+        int rc = issue_program(p, P, which, p.cap_stream, d_Zq);
+        count_launch((int)(before - spde_launch_count(0)));     // counted again at every replay
+        cudaGraph_t g = nullptr;
+        cudaError_t e = cudaStreamEndCapture(p.cap_stream, &g);
+        if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+        SPDE_CUDA_CHECK(e);
+        SPDE_CUDA_CHECK(cudaGraphInstantiate(&P.graph[which], g, 0));
+        cudaGraphDestroy(g);
+        P.graph_key[which] = key;
+    }
+    SPDE_CUDA_CHECK(cudaEventRecord(p.ev_in, st));
+    SPDE_CUDA_CHECK(cudaStreamWaitEvent(p.cap_stream, p.ev_in, 0));
+    SPDE_CUDA_CHECK(cudaGraphLaunch(P.graph[which], p.cap_stream));
+    SPDE_CUDA_CHECK(cudaEventRecord(p.ev_out, p.cap_stream));
+    SPDE_CUDA_CHECK(cudaStreamWaitEvent(st, p.ev_out, 0));
+    int nk = 0;
+    for (const Launch &L : P.launches) nk += L.kind != LK_ZERO;
+    count_launch(nk);
+    return SPDE_OK;
+}
+
 static int ensure_device(Plan &p, int which)
 {
+    init_gemm_attributes();
+    {
+        const char *env = getenv("SPDE_GRAPHS");
+        if (env) p.use_graphs = atoi(env);
+    }
     if (!(p.device_ready & 1)) {
         std::vector<int> idx(p.sym.rows);
         idx.insert(idx.end(), p.sym.relidx.begin(), p.sym.relidx.end());
@@ -412,7 +485,8 @@ extern "C" void spde_plan_destroy(spde_plan *pp)
     Plan *p = reinterpret_cast<Plan *>(pp);
     for (int a = 0; a < 2; a++) { cudaFree(p->d_L[a]); cudaFree(p->d_dinv[a]); cudaFree(p->d_arena[a]); cudaFree(p->d_zarena[a]); }
     cudaFree(p->d_ybuf); cudaFree(p->d_X); cudaFree(p->d_red); cudaFree(p->d_idx); cudaFree(p->d_qdest);
-    cudaFree(p->d_diagpos); cudaFree(p->d_cand); cudaFree(p->d_perm); cudaFree(p->d_status); cudaFree(p->d_zentries);
+    cudaFree(p->d_zq); cudaFree(p->d_diagpos); cudaFree(p->d_cand); cudaFree(p->d_perm); cudaFree(p->d_status); cudaFree(p->d_zentries);
+    if (p->cap_stream) { cudaStreamDestroy(p->cap_stream); cudaEventDestroy(p->ev_in); cudaEventDestroy(p->ev_out); }
     free_program(p->factor);
     free_program(p->selinv);
     for (auto &kv : p->solve) free_program(kv.second);
@@ -611,8 +685,13 @@ extern "C" int spde_selinv(spde_plan *pp, int which, double *d_Zq, void *stream)
         SPDE_CUDA_CHECK(upload(p.zentries, &p.d_zentries));
         p.device_ready |= 2;
     }
-    SPDE_CUDA_CHECK(cudaMemsetAsync(d_Zq, 0, (size_t)p.sym.nslots * p.sym.n * sizeof(double), st));
-    return run_program(p, p.selinv, which, st, d_Zq);
+    const size_t zbytes = (size_t)p.sym.nslots * p.sym.n * sizeof(double);
+    if (!p.d_zq) SPDE_CUDA_CHECK(cudaMalloc((void **)&p.d_zq, zbytes));
+    SPDE_CUDA_CHECK(cudaMemsetAsync(p.d_zq, 0, zbytes, st));
+    int rc = run_program(p, p.selinv, which, st, p.d_zq);
+    if (rc) return rc;
+    SPDE_CUDA_CHECK(cudaMemcpyAsync(d_Zq, p.d_zq, zbytes, cudaMemcpyDeviceToDevice, st));
+    return SPDE_OK;
 }
 
 // ---------------------------------------------------------------------------------------------

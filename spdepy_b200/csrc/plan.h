@@ -61,6 +61,10 @@ struct Program {
     ExtTask *d_ext = nullptr; GatherTask *d_gather = nullptr; WtwTask *d_wtw = nullptr;
     bool uploaded = false;
     double flops = 0;
+    // CUDA graph of the whole schedule, per factor store; re-captured when a base pointer changes
+    cudaGraphExec_t graph[2] = {nullptr, nullptr};
+    unsigned long long graph_key[2] = {0, 0};
+    int runs[2] = {0, 0};
 };
 
 struct ZEntry { long long dst, dst2; long long src; int sn, pad; };   // selected-inverse extraction
@@ -96,6 +100,12 @@ struct Plan {
     ZEntry *d_zentries = nullptr;
     int status[2] = {0, 0}, bad_col[2] = {-1, -1};
     bool factored[2] = {false, false};
+    // graph replay machinery: schedules are captured on a private stream and ordered against the caller's
+    // stream with two events (the caller's stream may be the legacy default stream, which cannot capture)
+    int use_graphs = 1;
+    cudaStream_t cap_stream = nullptr;
+    cudaEvent_t ev_in = nullptr, ev_out = nullptr;
+    double *d_zq = nullptr;
     // optional per-launch timing (CUDA events), accumulated per (launch kind, GEMM variant)
     bool prof_on = false;
     double prof_ms[8][16] = {{0}};

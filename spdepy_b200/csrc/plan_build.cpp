@@ -6,6 +6,7 @@
 // step sequence (GEMM / POTRF / ...); the heads of all sequences that share a kind are merged into
 // one grouped launch, so the launch count is ~ (levels x steps of the widest front), not ~ nsuper.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "plan.h"
@@ -123,11 +124,17 @@ namespace {
 constexpr int CFG_BM[3] = {128, 128, 64};
 constexpr int CFG_BN[3] = {128, 64, 64};
 
-int pick_cfg(int M, int N)
+// tile configuration of a grouped launch: the largest tile that still gives >= 2 CTAs per SM
+constexpr int kSMs = 148;
+long long count_tiles(const GemmTask &t, int cfg)
 {
-    if (N <= 64) return M >= 512 ? 1 : 2;
-    if (M >= 256 && N >= 128) return 0;
-    return 2;
+    const int BM = CFG_BM[cfg], BN = CFG_BN[cfg];
+    const int tm = (t.M + BM - 1) / BM, tn = (t.N + BN - 1) / BN;
+    if (!(t.flags & GF_LOWER)) return (long long)tm * tn;
+    long long c = 0;
+    for (int tj = 0; tj < tn; tj++)
+        for (int ti = 0; ti < tm; ti++) c += !((ti + 1) * BM - 1 < tj * BN);
+    return c;
 }
 
 struct Step {
@@ -161,8 +168,8 @@ struct LevelBuilder {
         Step st;
         memset(&st, 0, sizeof st);
         st.kind = LK_GEMM;
-        if (cfg < 0) cfg = pick_cfg(t.M, t.N);
-        st.variant = cfg * 4 + (akmaj ? 2 : 0) + (bkmaj ? 1 : 0);
+        // bits 0-1: operand layouts; bits 2-3: forced tile config + 1 (0 = choose per launch)
+        st.variant = ((cfg + 1) << 2) + (akmaj ? 2 : 0) + (bkmaj ? 1 : 0);
         st.g0 = (int)pool.size();
         st.gn = 1;
         pool.push_back(t);
@@ -176,9 +183,16 @@ struct LevelBuilder {
         s.back().gn++;
     }
 
-    void emit_gemm_launch(int variant, const std::vector<const Step *> &steps)
+    void emit_gemm_launch(int key, const std::vector<const Step *> &steps)
     {
-        const int cfg = variant / 4;
+        int cfg = (key >> 2) - 1;
+        if (cfg < 0) {
+            long long big = 0;
+            for (const Step *st : steps)
+                for (int g = st->g0; g < st->g0 + st->gn; g++) big += count_tiles(pool[g], 1);
+            cfg = big >= 2 * kSMs ? 1 : 2;
+        }
+        const int variant = cfg * 4 + (key & 3);
         const int BM = CFG_BM[cfg], BN = CFG_BN[cfg];
         Launch L;
         memset(&L, 0, sizeof L);
@@ -446,6 +460,8 @@ void Plan::build_selinv_program()
     selinv_built = true;
     Program &P = selinv;
     const Symbolic &S = sym;
+    const char *env = getenv("SPDE_SPLITK_MIN");          // test hook: exercise the split-K path on small meshes
+    const int splitk_min = env ? std::max(8, atoi(env)) : 2048;
     for (int d = 0; d <= S.maxdepth; d++) {
         const std::vector<int> &lev = by_depth[d];
         const int sp_z = SP_Z0 + (d & 1), sp_par = SP_Z0 + ((d + 1) & 1);
@@ -505,11 +521,23 @@ void Plan::build_selinv_program()
                 B.add_gemm(q, B.task(SP_L, x.panel + r0 + (int64_t)c0 * x.ld, x.ld, SP_DINV, W, NB,
                                      SP_Y, Y, ldy, mb, b, b, GF_BETA0), false, true);
                 // Z[below,p] = -Z[below,below] * Y   (and its transpose into the row block)
-                GemmTask t = B.task(sp_z, F + r0 + (int64_t)r0 * x.ld, x.ld, SP_Y, Y, ldy,
-                                    sp_z, F + r0 + (int64_t)c0 * x.ld, x.ld, mb, b, mb,
-                                    GF_BETA0 | GF_NEG | GF_UPPER_MIRROR);
-                t.c2 = F + c0 + (int64_t)r0 * x.ld;
-                B.add_gemm(q, t, false, true);
+                // Skinny product (N <= 64): for the big fronts near the root there are fewer row tiles than
+                // SMs, so K is split into chunks that accumulate atomically into the (still zero) block.
+                int nchunk = 1;
+                if (mb >= splitk_min) {
+                    const int rowtiles = (mb + 127) / 128;
+                    nchunk = std::max(1, std::min((2 * kSMs + rowtiles - 1) / rowtiles, mb / (splitk_min / 4)));
+                }
+                int clen = (mb + nchunk - 1) / nchunk;
+                clen += clen & 1;
+                for (int k0 = 0, ci = 0; k0 < mb; k0 += clen, ci++) {
+                    GemmTask t = B.task(sp_z, F + r0 + (int64_t)(r0 + k0) * x.ld, x.ld, SP_Y, Y + k0, ldy,
+                                        sp_z, F + r0 + (int64_t)c0 * x.ld, x.ld, mb, b, std::min(clen, mb - k0),
+                                        GF_NEG | GF_UPPER_MIRROR | (nchunk == 1 ? GF_BETA0 : GF_ATOMIC));
+                    t.c2 = F + c0 + (int64_t)r0 * x.ld;
+                    if (ci == 0) B.add_gemm(q, t, false, true);
+                    else B.join_gemm(q, t);
+                }
                 // Z_pp -= Y^T Z[below,p]   (split over K, accumulated atomically)
                 const int chunk = 2048;
                 bool opened = false;

@@ -138,3 +138,25 @@ def test_emulated_large_fronts(shape):
     full = pat.to_csc(Zq).toarray()
     mask = pat.to_csc(np.ones(pat.nslots * n)).toarray() != 0
     assert np.abs(full[mask] - Zd[mask]).max() < 1e-10 * np.abs(Zd).max()
+
+
+def test_emulated_selinv_split_k(monkeypatch):
+    """The split-K variant of the skinny Takahashi product (normally only for fronts >= 2048 rows)."""
+    monkeypatch.setenv("SPDE_SPLITK_MIN", "64")
+    M, N, T, bc = 20, 18, 6, 3
+    plan = _lib.PlanHandle(M, N, T, bc)
+    pat = Pattern(M, N, T, bc)
+    n = plan.n
+    rng = np.random.default_rng(2)
+    W = pat.to_csc(rng.normal(size=pat.nslots * n))
+    A = (W + W.T) * 0.5
+    A = sparse.csc_matrix(A + sparse.diags(np.abs(A).sum(axis=1).A1 + 1.0))
+    em = pe.Emulator(plan)
+    assert em.factorize(pat.from_sparse(A)) == 0
+    prog = pe.Program(plan, 3)
+    assert ((prog.gemm["flags"] & pe.GF_ATOMIC) != 0).sum() > (prog.gemm["flags"] & pe.GF_MIRROR != 0).sum() // 4
+    Zq = em.selinv()
+    Zd = np.linalg.inv(A.toarray())
+    full = pat.to_csc(Zq).toarray()
+    mask = pat.to_csc(np.ones(pat.nslots * n)).toarray() != 0
+    assert np.abs(full[mask] - Zd[mask]).max() < 1e-10 * np.abs(Zd).max()
