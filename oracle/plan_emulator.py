@@ -14,7 +14,7 @@ import numpy as np
 
 GF_LOWER, GF_BETA0, GF_NEG, GF_ATOMIC, GF_GATHER_A, GF_SCATTER_C, GF_MIRROR = (1 << 9, 1 << 10, 1 << 11, 1 << 12,
                                                                             1 << 13, 1 << 14, 1 << 15)
-LK_GEMM, LK_POTRF, LK_EXTADD, LK_ZERO, LK_GATHER, LK_WTW, LK_EXTRACT = range(7)
+LK_GEMM, LK_POTRF, LK_EXTADD, LK_ZERO, LK_GATHER, LK_WTW, LK_EXTRACT, LK_GEMV = range(8)
 NB = 64
 CFG = {0: (128, 128), 1: (128, 64), 2: (64, 64)}
 
@@ -72,9 +72,13 @@ class Emulator:
         buf = self.sp[space]
         return np.lib.stride_tricks.as_strided(buf[off:], shape=(rows, cols), strides=(8, 8 * ld), writeable=True)
 
-    def _gemm_launch(self, P, L):
-        cfg, ak, bk = L["variant"] // 4, (L["variant"] >> 1) & 1, L["variant"] & 1
-        BM, BN = CFG[cfg]
+    def _gemm_launch(self, P, L, gemv=False):
+        if gemv:    # k_gemv_grouped: all M rows, 256 / 64 columns per tile, K split in chunks of 1024 (tile.ti)
+            ak, bk = 0, int(L["variant"])
+            BM, BN = 1 << 30, (64 if bk else 256)
+        else:
+            cfg, ak, bk = L["variant"] // 4, (L["variant"] >> 1) & 1, L["variant"] & 1
+            BM, BN = CFG[cfg]
         tasks = P.gemm[L["task0"]:L["task0"] + L["ntasks"]]
         tiles = P.tiles[L["tile0"]:L["tile0"] + L["ntiles"]]
         # the CUDA kernel reads its operand tiles completely before writing C; emulate per tile
@@ -82,7 +86,14 @@ class Emulator:
             t = tasks[tr["task"]]
             f = int(t["flags"])
             M, N, K = int(t["M"]), int(t["N"]), int(t["K"])
-            i0, j0 = int(tr["ti"]) * BM, int(tr["tj"]) * BN
+            if gemv:
+                assert M <= 4
+                i0, j0 = 0, int(tr["tj"]) * BN
+                ka, kb = int(tr["ti"]) * 1024, min(K, int(tr["ti"]) * 1024 + 1024)
+                assert not (f & GF_BETA0) or K <= 1024
+            else:
+                i0, j0 = int(tr["ti"]) * BM, int(tr["tj"]) * BN
+                ka, kb = 0, K
             i1, j1 = min(i0 + BM, M), min(j0 + BN, N)
             sa, sb, sc = f & 7, (f >> 3) & 7, (f >> 6) & 7
             if ak:
@@ -97,7 +108,7 @@ class Emulator:
                 B = self._view(sb, int(t["b"]), int(t["ldb"]), K, N)[:, j0:j1]
             else:
                 B = self._view(sb, int(t["b"]), int(t["ldb"]), N, K)[j0:j1].T
-            prod = np.array(A) @ np.array(B)
+            prod = np.array(A)[:, ka:kb] @ np.array(B)[ka:kb]
             if f & GF_NEG:
                 prod = -prod
             ii, jj = np.meshgrid(np.arange(i0, i1), np.arange(j0, j1), indexing="ij")
@@ -189,6 +200,8 @@ class Emulator:
             kind = int(L["kind"])
             if kind == LK_GEMM:
                 self._gemm_launch(P, L)
+            elif kind == LK_GEMV:
+                self._gemm_launch(P, L, gemv=True)
             elif kind == LK_POTRF:
                 self._potrf(P, L)
             elif kind == LK_EXTADD:

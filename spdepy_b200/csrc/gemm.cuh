@@ -71,7 +71,9 @@ constexpr int gemm_smem_bytes()
     // worst case of the two layouts per operand
     constexpr int a = (BM + 4) * GEMM_BK > BM * (GEMM_BK + 4) ? (BM + 4) * GEMM_BK : BM * (GEMM_BK + 4);
     constexpr int b = (BN + 4) * GEMM_BK > BN * (GEMM_BK + 4) ? (BN + 4) * GEMM_BK : BN * (GEMM_BK + 4);
-    return GEMM_STAGES * (a + b) * 8;
+    constexpr int pipe = GEMM_STAGES * (a + b) * 8;
+    constexpr int epi = (BM + 2) * BN * 8;       // accumulator tile staged for the coalesced epilogue
+    return pipe > epi ? pipe : epi;
 }
 
 // Load one BT x BK operand tile into shared memory.
@@ -186,34 +188,159 @@ k_gemm_grouped(const GemmTask *__restrict__ tasks, const TileRef *__restrict__ t
     }
     cp_async_wait<0>();
 
-    // epilogue: each thread owns C[row = lane/4][cols 2*(lane%4), +1] of every 8x8 tile
-    double *gC = sp.base[(tk.flags >> 6) & 7] + tk.c;
-    const int *scat = (tk.flags & GF_SCATTER_C) ? sp.idx + tk.cidx : nullptr;
+    // epilogue: accumulators -> shared memory (column-major tile, LD = BM+2 keeps the stores conflict
+    // free) -> coalesced 16-byte read-modify-write of C.  Each thread owns C[row = lane/4][cols 2*(lane%4), +1]
+    // of every 8x8 DMMA tile, which would be 8-byte strided accesses if written straight to global memory.
+    constexpr int LDS = BM + 2;
+    double *sC = smem;
+    __syncthreads();      // every warp is done with the operand stages
     const bool neg = tk.flags & GF_NEG, beta0 = tk.flags & GF_BETA0, lower = tk.flags & GF_LOWER;
     const bool atomic = tk.flags & GF_ATOMIC, mirror = tk.flags & GF_UPPER_MIRROR;
 #pragma unroll
-    for (int a = 0; a < MT; a++) {
-        const int r = i0 + wm * WM + a * 8 + lr;
-        if (r >= tk.M) continue;
+    for (int a = 0; a < MT; a++)
 #pragma unroll
-        for (int b = 0; b < NTL; b++) {
+        for (int b = 0; b < NTL; b++)
 #pragma unroll
             for (int e = 0; e < 2; e++) {
-                const int c = j0 + wn * WN + b * 8 + lc * 2 + e;
-                if (c >= tk.N) continue;
-                if (lower && r < c) continue;
                 const double v = neg ? -acc[a][b][e] : acc[a][b][e];
-                const long long col = scat ? (long long)scat[c] : (long long)c;
-                double *p = gC + r + col * tk.ldc;
-                if (atomic) atomicAdd(p, v);
-                else if (beta0) *p = v;
-                else *p += v;
-                if (mirror) {
-                    double *q = gC - tk.c + tk.c2 + c + (long long)r * tk.ldc;
-                    if (atomic) atomicAdd(q, v);
-                    else if (beta0) *q = v;
-                    else *q += v;
+                sC[(wn * WN + b * 8 + lc * 2 + e) * LDS + (wm * WM + a * 8 + lr)] = v;
+            }
+    __syncthreads();
+    double *gC = sp.base[(tk.flags >> 6) & 7] + tk.c;
+    const int *scat = (tk.flags & GF_SCATTER_C) ? sp.idx + tk.cidx : nullptr;
+    const int mrows = min(BM, tk.M - i0), ncols = min(BN, tk.N - j0);
+    constexpr int RP = BM / 2;                 // row pairs per column
+    for (int id = tid; id < RP * BN; id += NT) {
+        const int cl = id / RP, rl = (id % RP) * 2;
+        if (cl >= ncols || rl >= mrows) continue;
+        const int r = i0 + rl, c = j0 + cl;
+        const bool two = rl + 1 < mrows;
+        bool w0 = true, w1 = two;
+        if (lower) { w0 = r >= c; w1 = two && (r + 1 >= c); }
+        if (!w0 && !w1) continue;
+        const double v0 = sC[cl * LDS + rl], v1 = sC[cl * LDS + rl + 1];
+        const long long col = scat ? (long long)scat[c] : (long long)c;
+        double *p = gC + r + col * tk.ldc;
+        if (atomic) {
+            if (w0) atomicAdd(p, v0);
+            if (w1) atomicAdd(p + 1, v1);
+        } else if (w0 && w1 && ((reinterpret_cast<uintptr_t>(p) & 15) == 0)) {
+            double2 o = beta0 ? make_double2(0.0, 0.0) : *reinterpret_cast<const double2 *>(p);
+            o.x += v0; o.y += v1;
+            *reinterpret_cast<double2 *>(p) = o;
+        } else {
+            if (w0) p[0] = beta0 ? v0 : p[0] + v0;
+            if (w1) p[1] = beta0 ? v1 : p[1] + v1;
+        }
+    }
+    if (mirror) {
+        // transposed copy: element (r,c) also goes to c2 + c + r*ldc, contiguous in c
+        double *gM = sp.base[(tk.flags >> 6) & 7] + tk.c2;
+        constexpr int CP = BN / 2;
+        for (int id = tid; id < CP * BM; id += NT) {
+            const int rl = id / CP, cl = (id % CP) * 2;
+            if (rl >= mrows || cl >= ncols) continue;
+            const bool two = cl + 1 < ncols;
+            const double v0 = sC[cl * LDS + rl], v1 = two ? sC[(cl + 1) * LDS + rl] : 0.0;
+            double *q = gM + (j0 + cl) + (long long)(i0 + rl) * tk.ldc;
+            if (atomic) {
+                atomicAdd(q, v0);
+                if (two) atomicAdd(q + 1, v1);
+            } else if (two && ((reinterpret_cast<uintptr_t>(q) & 15) == 0)) {
+                double2 o = beta0 ? make_double2(0.0, 0.0) : *reinterpret_cast<const double2 *>(q);
+                o.x += v0; o.y += v1;
+                *reinterpret_cast<double2 *>(q) = o;
+            } else {
+                q[0] = beta0 ? v0 : q[0] + v0;
+                if (two) q[1] = beta0 ? v1 : q[1] + v1;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Small-M variant (M <= 4 right-hand sides): the triangular solves for the conditional mean have one
+// column per data replicate, where a 64x64 tensor-core tile would waste 63/64 of its rows.  These
+// are HBM-bound matrix-vector products: every element of L is read exactly once, coalesced, and K is
+// split across CTAs (atomic accumulation) so that a single wide front still fills the machine.
+//   B_KMAJ=false: B(j,kk) at b + j + kk*ldb -> one thread per output column j (256 columns per tile)
+//   B_KMAJ=true : B(j,kk) at b + kk + j*ldb -> one warp per output column, lanes stride over kk (64 columns per tile)
+constexpr int GEMV_KC = 1024;
+
+template <bool B_KMAJ>
+__global__ void __launch_bounds__(256) k_gemv_grouped(const GemmTask *__restrict__ tasks, const TileRef *__restrict__ tiles,
+                                                      GemmSpaces sp)
+{
+    const TileRef tr = tiles[blockIdx.x];
+    const GemmTask tk = tasks[tr.task];
+    const int tid = threadIdx.x;
+    const int k0 = tr.ti * GEMV_KC, k1 = min(tk.K, k0 + GEMV_KC);
+    const double *gA = sp.base[tk.flags & 7] + tk.a;
+    const double *gB = sp.base[(tk.flags >> 3) & 7] + tk.b;
+    double *gC = sp.base[(tk.flags >> 6) & 7] + tk.c;
+    const int *gather = (tk.flags & GF_GATHER_A) ? sp.idx + tk.aidx : nullptr;
+    const int *scat = (tk.flags & GF_SCATTER_C) ? sp.idx + tk.cidx : nullptr;
+    const bool neg = tk.flags & GF_NEG, beta0 = tk.flags & GF_BETA0;
+    const int M = tk.M;
+    if (!B_KMAJ) {
+        const int j = tr.tj * 256 + tid;
+        const bool live = j < tk.N;
+        double acc[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int kk = k0; kk < k1; kk++) {
+            const double bv = live ? gB[j + (long long)kk * tk.ldb] : 0.0;
+            const long long col = gather ? (long long)gather[kk] : (long long)kk;
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+                if (i < M) acc[i] += gA[i + col * tk.lda] * bv;
+        }
+        if (beta0) __syncthreads();          // in-place tasks (C aliases A): all reads precede all writes
+        if (live) {
+            const long long ccol = scat ? (long long)scat[j] : (long long)j;
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+                if (i < M) {
+                    const double v = neg ? -acc[i] : acc[i];
+                    double *p = gC + i + ccol * tk.ldc;
+                    if (beta0) *p = v; else atomicAdd(p, v);
                 }
+        }
+    } else {
+        const int w = tid >> 5, lane = tid & 31;
+        double res[8][4];
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+            const int j = tr.tj * 64 + w * 8 + c;
+            double acc[4] = {0.0, 0.0, 0.0, 0.0};
+            if (j < tk.N) {
+                for (int kk = k0 + lane; kk < k1; kk += 32) {
+                    const double bv = gB[kk + (long long)j * tk.ldb];
+                    const long long col = gather ? (long long)gather[kk] : (long long)kk;
+#pragma unroll
+                    for (int i = 0; i < 4; i++)
+                        if (i < M) acc[i] += gA[i + col * tk.lda] * bv;
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                double s = acc[i];
+                for (int o = 16; o; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+                res[c][i] = s;
+            }
+        }
+        if (beta0) __syncthreads();
+        if (lane == 0) {
+#pragma unroll
+            for (int c = 0; c < 8; c++) {
+                const int j = tr.tj * 64 + w * 8 + c;
+                if (j >= tk.N) continue;
+                const long long ccol = scat ? (long long)scat[j] : (long long)j;
+#pragma unroll
+                for (int i = 0; i < 4; i++)
+                    if (i < M) {
+                        const double v = neg ? -res[c][i] : res[c][i];
+                        double *p = gC + i + ccol * tk.ldc;
+                        if (beta0) *p = v; else atomicAdd(p, v);
+                    }
             }
         }
     }

@@ -82,21 +82,21 @@ __global__ void __launch_bounds__(256) k_potrf(const PotrfTask *__restrict__ tas
     }
     if (tid < NB) wd[tid] = 0.0;
     __syncthreads();
-    for (int j = 0; j < b; j++) {
-        if (tid == 0) {
+    // Right-looking sweep, one barrier per column: every thread owns row i = tid % 64 and a quarter of
+    // the columns; the pivot sqrt / reciprocal are recomputed by all threads instead of broadcast.
+    {
+        const int i = tid & 63, ty = tid >> 6;
+        for (int j = 0; j < b; j++) {
             const double d = a[j][j];
-            if (!(d > 0.0)) { if (bad < 0) bad = j; a[j][j] = nan(""); }
-            else a[j][j] = sqrt(d);
-        }
-        __syncthreads();
-        const double ljj = a[j][j];
-        for (int i = j + 1 + tid; i < b; i += 256) a[i][j] /= ljj;
-        __syncthreads();
-        // trailing update: (i,c) with j < c <= i < b
-        const int rem = b - j - 1;
-        for (int e = tid; e < rem * rem; e += 256) {
-            const int i = j + 1 + e % rem, c = j + 1 + e / rem;
-            if (c <= i) a[i][c] -= a[i][j] * a[c][j];
+            const bool ok = d > 0.0;
+            const double ljj = ok ? sqrt(d) : nan("");
+            const double inv = 1.0 / ljj;
+            const double li = (i > j && i < b) ? a[i][j] * inv : 0.0;
+            if (i > j && i < b)
+                for (int c = j + 1 + ty; c <= i; c += 4) a[i][c] -= li * (a[c][j] * inv);
+            __syncthreads();                       // column j has been read by everyone
+            if (ty == 0 && i > j && i < b) a[i][j] = li;
+            if (tid == 0) { a[j][j] = ljj; if (!ok && bad < 0) bad = j; }
         }
         __syncthreads();
     }
@@ -326,6 +326,10 @@ static int issue_program(Plan &p, Program &P, int which, cudaStream_t st, double
         case LK_GEMM:
             SPDE_CUDA_CHECK(launch_gemm(L, P, sp, st));
             break;
+        case LK_GEMV:
+            if (L.variant) k_gemv_grouped<true><<<L.ntiles, 256, 0, st>>>(P.d_gemm + L.task0, P.d_tiles + L.tile0, sp);
+            else k_gemv_grouped<false><<<L.ntiles, 256, 0, st>>>(P.d_gemm + L.task0, P.d_tiles + L.tile0, sp);
+            break;
         case LK_POTRF:
             k_potrf<<<L.ntasks, 256, 0, st>>>(P.d_potrf + L.task0, p.d_L[which], p.d_dinv[which], p.d_status);
             break;
@@ -353,9 +357,11 @@ static int issue_program(Plan &p, Program &P, int which, cudaStream_t st, double
     }
     if (p.prof_on) {
         SPDE_CUDA_CHECK(cudaStreamSynchronize(st));
+        P.last_ms.assign(P.launches.size(), 0.f);
         for (size_t i = 0; i < P.launches.size(); i++) {
             float ms = 0.f;
             cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
+            P.last_ms[i] = ms;
             const Launch &L = P.launches[i];
             const int v = L.kind == LK_GEMM ? L.variant : 0;
             p.prof_ms[L.kind][v] += ms;
@@ -560,6 +566,7 @@ extern "C" int spde_plan_export(spde_plan *pp, int prog, int k, int what, void *
         case 4: EXP(P->ext) break;
         case 5: EXP(P->gather) break;
         case 6: EXP(P->wtw) break;
+        case 7: EXP(P->last_ms) break;
         default: set_error("spde_plan_export: bad what"); return SPDE_ERR_ARG;
         }
     } else if (prog == 4) {   // layout

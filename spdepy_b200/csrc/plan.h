@@ -39,7 +39,7 @@ struct GatherTask {   // selected inverse: child's trailing block <- parent's fr
 };
 struct WtwTask { long long w; long long dst; int ldd, b, space, pad; };
 
-enum LaunchKind : int { LK_GEMM = 0, LK_POTRF, LK_EXTADD, LK_ZERO, LK_GATHER, LK_WTW, LK_EXTRACT };
+enum LaunchKind : int { LK_GEMM = 0, LK_POTRF, LK_EXTADD, LK_ZERO, LK_GATHER, LK_WTW, LK_EXTRACT, LK_GEMV };
 
 struct Launch {
     int kind, variant;
@@ -65,6 +65,7 @@ struct Program {
     cudaGraphExec_t graph[2] = {nullptr, nullptr};
     unsigned long long graph_key[2] = {0, 0};
     int runs[2] = {0, 0};
+    std::vector<float> last_ms;   // per-launch device time of the last profiled run
 };
 
 struct ZEntry { long long dst, dst2; long long src; int sn, pad; };   // selected-inverse extraction

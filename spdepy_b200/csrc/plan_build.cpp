@@ -175,6 +175,49 @@ struct LevelBuilder {
         pool.push_back(t);
         s.push_back(st);
     }
+    // small-M (k <= 4 right-hand sides) matrix-vector step; variant = B layout
+    void add_gemv(std::vector<Step> &s, const GemmTask &t, bool bkmaj)
+    {
+        if (t.M <= 0 || t.N <= 0 || t.K <= 0) return;
+        Step st;
+        memset(&st, 0, sizeof st);
+        st.kind = LK_GEMV;
+        st.variant = bkmaj ? 1 : 0;
+        st.g0 = (int)pool.size();
+        st.gn = 1;
+        pool.push_back(t);
+        s.push_back(st);
+    }
+    // dense step of a solve: tensor-core GEMM, or the matrix-vector kernel when there are <= 4 columns
+    void add_solve(std::vector<Step> &s, const GemmTask &t, bool bkmaj)
+    {
+        if (t.M <= 4) add_gemv(s, t, bkmaj);
+        else add_gemm(s, t, false, bkmaj);
+    }
+    void emit_gemv_launch(int bk, const std::vector<const Step *> &steps)
+    {
+        const int TN = bk ? 64 : 256, KC = 1024;
+        Launch L;
+        memset(&L, 0, sizeof L);
+        L.kind = LK_GEMV;
+        L.variant = bk;
+        L.task0 = (int64_t)prog.gemm.size();
+        L.tile0 = (int64_t)prog.tiles.size();
+        for (const Step *st : steps)
+            for (int g = st->g0; g < st->g0 + st->gn; g++) {
+                const GemmTask &t = pool[g];
+                const int id = (int)(prog.gemm.size() - L.task0);
+                prog.gemm.push_back(t);
+                const int tn = (t.N + TN - 1) / TN, tk = (t.K + KC - 1) / KC;
+                for (int kc = 0; kc < tk; kc++)
+                    for (int tj = 0; tj < tn; tj++) prog.tiles.push_back(TileRef{id, kc, tj, 0});
+                prog.flops += 2.0 * t.M * t.N * t.K;
+            }
+        L.ntasks = (int)(prog.gemm.size() - L.task0);
+        L.ntiles = (int)(prog.tiles.size() - L.tile0);
+        if (L.ntiles > 0) prog.launches.push_back(L);
+    }
+
     // append `t` to the previous GEMM step (same variant) instead of opening a new step
     void join_gemm(std::vector<Step> &s, const GemmTask &t)
     {
@@ -230,7 +273,7 @@ struct LevelBuilder {
             // pick the (kind, variant) shared by most heads
             std::map<std::pair<int, int>, int> votes;
             for (size_t i = 0; i < m; i++)
-                if (head[i] < seq[i].size()) votes[{seq[i][head[i]].kind, seq[i][head[i]].kind == LK_GEMM ? seq[i][head[i]].variant : 0}]++;
+                if (head[i] < seq[i].size()) votes[{seq[i][head[i]].kind, (seq[i][head[i]].kind == LK_GEMM || seq[i][head[i]].kind == LK_GEMV) ? seq[i][head[i]].variant : 0}]++;
             std::pair<int, int> best{-1, -1};
             int bv = -1;
             for (auto &kv : votes) if (kv.second > bv) { bv = kv.second; best = kv.first; }
@@ -239,13 +282,15 @@ struct LevelBuilder {
                 if (head[i] >= seq[i].size()) continue;
                 const Step &st = seq[i][head[i]];
                 if (st.kind != best.first) continue;
-                if (st.kind == LK_GEMM && st.variant != best.second) continue;
+                if ((st.kind == LK_GEMM || st.kind == LK_GEMV) && st.variant != best.second) continue;
                 chosen.push_back(&st);
                 head[i]++;
                 remaining--;
             }
             if (best.first == LK_GEMM) {
                 emit_gemm_launch(best.second, chosen);
+            } else if (best.first == LK_GEMV) {
+                emit_gemv_launch(best.second, chosen);
             } else if (best.first == LK_POTRF) {
                 Launch L;
                 memset(&L, 0, sizeof L);
@@ -402,20 +447,20 @@ Program &Plan::solve_program(int k, int dir)
                 for (int p = 0; p < x.nblk; p++) {
                     const int c0 = p * NB, b = std::min(NB, x.nc - c0);
                     // y_p = x_p W_p^T (in place)
-                    B.add_gemm(q, B.task(SP_X, xs + (int64_t)c0 * kp, kp, SP_DINV, x.dinv + (int64_t)p * NB * NB, NB,
-                                         SP_X, xs + (int64_t)c0 * kp, kp, k, b, b, GF_BETA0), false, false);
+                    B.add_solve(q, B.task(SP_X, xs + (int64_t)c0 * kp, kp, SP_DINV, x.dinv + (int64_t)p * NB * NB, NB,
+                                         SP_X, xs + (int64_t)c0 * kp, kp, k, b, b, GF_BETA0), false);
                     // remaining pivot columns of this supernode
                     const int rest = x.nc - c0 - b;
                     if (rest > 0)
-                        B.add_gemm(q, B.task(SP_X, xs + (int64_t)c0 * kp, kp,
+                        B.add_solve(q, B.task(SP_X, xs + (int64_t)c0 * kp, kp,
                                              SP_L, x.panel + (c0 + b) + (int64_t)c0 * x.ld, x.ld,
-                                             SP_X, xs + (int64_t)(c0 + b) * kp, kp, k, rest, b, GF_NEG), false, false);
+                                             SP_X, xs + (int64_t)(c0 + b) * kp, kp, k, rest, b, GF_NEG), false);
                 }
                 if (x.nr > 0) {
                     GemmTask t = B.task(SP_X, xs, kp, SP_L, x.panel + x.ncp, x.ld, SP_X, 0, kp, k, x.nr, x.nc,
                                         GF_NEG | GF_SCATTER_C | GF_ATOMIC);
                     t.cidx = (int)x.rows;
-                    B.add_gemm(q, t, false, false);
+                    B.add_solve(q, t, false);
                 }
                 B.seq.push_back(std::move(q));
             }
@@ -433,18 +478,18 @@ Program &Plan::solve_program(int k, int dir)
                     GemmTask t = B.task(SP_X, 0, kp, SP_L, x.panel + x.ncp, x.ld, SP_X, xs, kp, k, x.nc, x.nr,
                                         GF_NEG | GF_GATHER_A);
                     t.aidx = (int)x.rows;
-                    B.add_gemm(q, t, false, true);
+                    B.add_solve(q, t, true);
                 }
                 for (int p = x.nblk - 1; p >= 0; p--) {
                     const int c0 = p * NB, b = std::min(NB, x.nc - c0);
                     const int later = x.nc - c0 - b;
                     if (later > 0)   // x_p -= X[later pivot columns] * L[later, p]
-                        B.add_gemm(q, B.task(SP_X, xs + (int64_t)(c0 + b) * kp, kp,
+                        B.add_solve(q, B.task(SP_X, xs + (int64_t)(c0 + b) * kp, kp,
                                              SP_L, x.panel + (c0 + b) + (int64_t)c0 * x.ld, x.ld,
-                                             SP_X, xs + (int64_t)c0 * kp, kp, k, b, later, GF_NEG), false, true);
+                                             SP_X, xs + (int64_t)c0 * kp, kp, k, b, later, GF_NEG), true);
                     // x_p = y_p W_p (in place)
-                    B.add_gemm(q, B.task(SP_X, xs + (int64_t)c0 * kp, kp, SP_DINV, x.dinv + (int64_t)p * NB * NB, NB,
-                                         SP_X, xs + (int64_t)c0 * kp, kp, k, b, b, GF_BETA0), false, true);
+                    B.add_solve(q, B.task(SP_X, xs + (int64_t)c0 * kp, kp, SP_DINV, x.dinv + (int64_t)p * NB * NB, NB,
+                                         SP_X, xs + (int64_t)c0 * kp, kp, k, b, b, GF_BETA0), true);
                 }
                 B.seq.push_back(std::move(q));
             }

@@ -1,0 +1,60 @@
+"""Per-launch device times of the factorisation / Takahashi schedules (CUDA events, spde_plan_profile),
+joined with the scheduled flops and tile counts of each launch.  Run on the GPU box:
+    python tools/launch_profile.py c3 > profiles/rNN_launch_profile_c3.txt"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import numpy as np
+import torch
+
+import bench
+import plan_emulator as pe
+
+name = sys.argv[1] if len(sys.argv) > 1 else "c3"
+inp = bench.make_inputs(name)
+mod = bench.build_ours(inp)
+m = mod.mod
+m.initFit(inp["data"], idx=inp["idx"])
+m.logLike(inp["theta"], grad=True, exact_grad=True)        # warm
+plan = m.engine.plan
+plan.profile(True)
+m.logLike(inp["theta"], grad=True, exact_grad=True)
+torch.cuda.synchronize()
+pms, pcnt = plan.profile(False)
+kinds = ["gemm", "potrf", "extend_add", "memset", "gather", "wtw", "extract"]
+print("# per kind ms:", {k: round(float(pms[i].sum()), 2) for i, k in enumerate(kinds)})
+print("# gemm by variant (cfg*4+ak*2+bk) ms:", {v: round(float(pms[0][v]), 2) for v in range(16) if pms[0][v] > 0})
+for prog, pname in ((0, "factor"), (3, "selinv")):
+    P = pe.Program(plan, prog)
+    ms = plan.export(prog, 7, "f4")
+    g = P.gemm
+    fl = 2.0 * g["M"] * g["N"] * g["K"] * np.where(g["flags"] & pe.GF_LOWER, 0.5, 1.0)
+    rows = []
+    for i, L in enumerate(P.launches):
+        if L["kind"] != 0:
+            continue
+        t = g[L["task0"]:L["task0"] + L["ntasks"]]
+        f = fl[L["task0"]:L["task0"] + L["ntasks"]].sum()
+        rows.append((ms[i], f, L["ntiles"], L["ntasks"], L["variant"], int(t["M"].max()), int(t["N"].max()), int(t["K"].max())))
+    rows = np.array(rows)
+    tot_ms, tot_f = rows[:, 0].sum(), rows[:, 1].sum()
+    print("\n## %s: %d gemm launches, %.1f ms, %.3g flop -> %.2f TFLOP/s (last profiled run of this schedule)"
+          % (pname, len(rows), tot_ms, tot_f, tot_f / tot_ms / 1e9))
+    # bucket by achieved rate
+    order = np.argsort(-rows[:, 0])
+    print("top 25 launches by time:  ms   TFLOP/s  tiles tasks variant  maxM  maxN  maxK")
+    for r in rows[order[:25]]:
+        print("   %8.3f %8.2f %7d %5d %5d %7d %5d %6d" % (r[0], r[1] / r[0] / 1e9, r[2], r[3], r[4], r[5], r[6], r[7]))
+    for lab, msk in (("N<=64,K<=64", (rows[:, 6] <= 64) & (rows[:, 7] <= 64)), ("N<=64,K>64", (rows[:, 6] <= 64) & (rows[:, 7] > 64)),
+                     ("N>64,K<=256", (rows[:, 6] > 64) & (rows[:, 7] <= 256)), ("N>64,K>256", (rows[:, 6] > 64) & (rows[:, 7] > 256))):
+        if msk.any():
+            print("   class %-12s launches %5d  ms %9.2f  flop %.3g  -> %.2f TFLOP/s" % (lab, msk.sum(), rows[msk, 0].sum(), rows[msk, 1].sum(),
+                                                                                         rows[msk, 1].sum() / max(rows[msk, 0].sum(), 1e-9) / 1e9))
+    other = [(kinds[L["kind"]], ms[i]) for i, L in enumerate(P.launches) if L["kind"] != 0]
+    agg = {}
+    for k, v in other:
+        agg[k] = agg.get(k, 0.0) + float(v)
+    print("   non-gemm ms:", {k: round(v, 2) for k, v in agg.items()})
