@@ -168,6 +168,12 @@ int spde_sddmm(int M, int N, int T, int bc, const double *d_X, const double *d_Y
 int spde_assembly_adjoint(int M, int N, int T, int bc, const double *d_W, const double *d_A9,
                           const double *d_kappa, int kvar, double V, double sigma, double dt, int timed,
                           double *d_work, double *d_GA9, double *d_Gq, double *d_GQ0_25, void *stream);
+/* Adjoints of the face-field stencils (transposes of spde_ah_stencil with face=1 and of spde_aw_stencil
+ * with face=1 in derivative mode): from d_GA9 = dS/dA9 to d_GH8[8][Ns] = dS/d(W00,E00,W10,E10,S01,N01,S11,N11),
+ * the eight tensor components AH_2D_b*.cpp reads, and d_GdG[Ns][4] = dS/d(dG of faces E,N,W,S) for the
+ * velocity field d_G (NaN-to-zero filter and boundary rules of Aw_2D_b*.cpp included).  Either output may be NULL. */
+int spde_stencil_adjoint(int M, int N, int bc, double hx, double hy, const double *d_GA9, double *d_GH8,
+                         const double *d_G, double *d_GdG, void *stream);
 /* d_out[c] = sum_r B[r,c] * u[r], B row-major rows x cols (spline-basis chain rule, evalB/evalBH). */
 int spde_gemv_t(const double *d_B, const double *d_u, int rows, int cols, double *d_out, void *stream);
 

@@ -339,9 +339,110 @@ __global__ void k_fill_spacetime(Geo g, const double *__restrict__ AtDA, const d
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Adjoints of the two face-field stencils (transpose of k_ah_stencil / k_aw_stencil in derivative
+// mode).  Given GA9 = d S / d A9 they return d S / d (the eight tensor components the diffusion
+// stencil reads) and d S / d (dG of each face), so the gradient with respect to *all* spline
+// coefficients is a handful of element-wise products and three small GEMVs with the spline bases
+// instead of one stencil evaluation per coefficient.
+__global__ void k_ah_adjoint(Geo g, double hx, double hy, const double *__restrict__ GA, double *__restrict__ GH)
+{
+    const int Ns = g.M * g.N;
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= Ns) return;
+    const int i = k % g.M, j = k / g.M;
+    double ga[9];
+#pragma unroll
+    for (int s = 0; s < 9; s++) ga[s] = GA[(size_t)s * Ns + k];
+    double gw[9];
+    gw[0] = ga[4];
+#pragma unroll
+    for (int s = 1; s < 9; s++) {
+        const int di = c_rdi[s], dj = c_rdj[s];
+        if (g.bc == 1) {
+            const int ii = min(max(i + di, 0), g.M - 1), jj = min(max(j + dj, 0), g.N - 1);
+            gw[s] = ga[gslot(ii - i, jj - j)];        // self-target (deleted, folded into rem) reads the centre
+        } else if (g.bc == 3) {
+            gw[s] = g.nbr(i, j, di, dj) >= 0 ? ga[gslot(di, dj)] : 0.0;
+        } else {
+            gw[s] = ga[gslot(di, dj)];
+        }
+    }
+    const double rx = hy / hx, ry = hx / hy;
+    double W00 = rx * (gw[2] - gw[0]), E00 = rx * (gw[1] - gw[0]);
+    double S11 = ry * (gw[4] - gw[0]), N11 = ry * (gw[3] - gw[0]);
+    double N01 = 0.25 * (gw[1] - gw[2] + gw[5] - gw[7]);
+    double S01 = 0.25 * (-gw[1] + gw[2] + gw[6] - gw[8]);
+    double E10 = 0.25 * (gw[3] - gw[4] + gw[5] - gw[8]);
+    double W10 = 0.25 * (-gw[3] + gw[4] + gw[6] - gw[7]);
+    if (g.bc == 1 && k == 0) { W00 = 0.0; W10 = 0.0; S11 = 0.0; S01 = 0.0; }   // stale-k zeroing (App. C-1)
+    GH[(size_t)0 * Ns + k] = W00; GH[(size_t)1 * Ns + k] = E00;
+    GH[(size_t)2 * Ns + k] = W10; GH[(size_t)3 * Ns + k] = E10;
+    GH[(size_t)4 * Ns + k] = S01; GH[(size_t)5 * Ns + k] = N01;
+    GH[(size_t)6 * Ns + k] = S11; GH[(size_t)7 * Ns + k] = N11;
+}
+
+// GdG[k][f]: adjoint of the derivative-mode advection stencil (diff=1 for faces E,W; diff=2 for N,S)
+__global__ void k_aw_adjoint(Geo g, double hx, double hy, const double *__restrict__ G, const double *__restrict__ GA,
+                             double *__restrict__ GdG)
+{
+    const int Ns = g.M * g.N;
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= Ns) return;
+    const int i = k % g.M, j = k / g.M;
+    const bool xe = (i == g.M - 1), xw = (i == 0), yn = (j == g.N - 1), ys = (j == 0);
+    double gf[4];
+#pragma unroll
+    for (int f = 0; f < 4; f++) gf[f] = G[(size_t)k * 4 + f];
+    if (g.bc == 1) { if (xe) gf[0] = 0.0; if (xw) gf[2] = 0.0; if (yn) gf[1] = 0.0; if (ys) gf[3] = 0.0; }
+    const double gC = GA[(size_t)4 * Ns + k];
+    const double gE = GA[(size_t)5 * Ns + k], gWs = GA[(size_t)3 * Ns + k], gN = GA[(size_t)7 * Ns + k], gS = GA[(size_t)1 * Ns + k];
+    const bool cut = g.bc != 2;
+    const double s0 = gf[0] / fabs(gf[0]), s2 = gf[2] / fabs(gf[2]), s1 = gf[1] / fabs(gf[1]), s3 = gf[3] / fabs(gf[3]);
+    // x faces (diff = 1)
+    {
+        const bool m0 = !(isnan(s0) || isnan(s2));
+        const bool mE = !isnan(s0) && !(cut && xe), mW = !isnan(s2) && !(cut && xw);
+        double d0 = 0.0, d2 = 0.0;
+        if (m0) { d0 += (s0 + 1.0) * gC; d2 += (s2 - 1.0) * gC; }
+        if (mE) d0 -= (s0 - 1.0) * gE;
+        if (mW) d2 -= (s2 + 1.0) * gWs;
+        GdG[(size_t)k * 4 + 0] = isnan(d0) ? 0.0 : d0 * hy / 2;
+        GdG[(size_t)k * 4 + 2] = isnan(d2) ? 0.0 : d2 * hy / 2;
+    }
+    // y faces (diff = 2)
+    {
+        const bool m0 = !(isnan(s1) || isnan(s3));
+        const bool mN = !isnan(s1) && !(cut && yn), mS = !isnan(s3) && !(cut && ys);
+        double d1 = 0.0, d3 = 0.0;
+        if (m0) { d1 += (s1 + 1.0) * gC; d3 += (s3 - 1.0) * gC; }
+        if (mN) d1 -= (s1 - 1.0) * gN;
+        if (mS) d3 -= (s3 + 1.0) * gS;
+        GdG[(size_t)k * 4 + 1] = isnan(d1) ? 0.0 : d1 * hx / 2;
+        GdG[(size_t)k * 4 + 3] = isnan(d3) ? 0.0 : d3 * hx / 2;
+    }
+}
+
 }  // namespace spde
 
 using namespace spde;
+
+extern "C" int spde_stencil_adjoint(int M, int N, int bc, double hx, double hy, const double *d_GA9, double *d_GH8,
+                                    const double *d_G, double *d_GdG, void *stream)
+{
+    Geo g{M, N, 1, bc};
+    if (d_GH8) {
+        k_ah_adjoint<<<cdiv(M * N, 128), 128, 0, (cudaStream_t)stream>>>(g, hx, hy, d_GA9, d_GH8);
+        count_launch();
+    }
+    if (d_G && d_GdG) {
+        k_aw_adjoint<<<cdiv(M * N, 128), 128, 0, (cudaStream_t)stream>>>(g, hx, hy, d_G, d_GA9, d_GdG);
+        count_launch();
+    }
+    SPDE_LAUNCH_CHECK();
+    return SPDE_OK;
+}
+
 
 extern "C" int spde_ah_stencil(int M, int N, int bc, double hx, double hy, const double *d_H, int face,
                                double *d_ah9, void *stream)

@@ -271,10 +271,11 @@ template <bool B_KMAJ>
 __global__ void __launch_bounds__(256) k_gemv_grouped(const GemmTask *__restrict__ tasks, const TileRef *__restrict__ tiles,
                                                       GemmSpaces sp)
 {
+    __shared__ double sA[4][GEMV_KC];        // the right-hand-side slice of this K chunk (<= 4 columns)
     const TileRef tr = tiles[blockIdx.x];
     const GemmTask tk = tasks[tr.task];
     const int tid = threadIdx.x;
-    const int k0 = tr.ti * GEMV_KC, k1 = min(tk.K, k0 + GEMV_KC);
+    const int k0 = tr.ti * GEMV_KC, kn = min(tk.K, k0 + GEMV_KC) - k0;
     const double *gA = sp.base[tk.flags & 7] + tk.a;
     const double *gB = sp.base[(tk.flags >> 3) & 7] + tk.b;
     double *gC = sp.base[(tk.flags >> 6) & 7] + tk.c;
@@ -282,62 +283,73 @@ __global__ void __launch_bounds__(256) k_gemv_grouped(const GemmTask *__restrict
     const int *scat = (tk.flags & GF_SCATTER_C) ? sp.idx + tk.cidx : nullptr;
     const bool neg = tk.flags & GF_NEG, beta0 = tk.flags & GF_BETA0;
     const int M = tk.M;
+    for (int e = tid; e < kn * M; e += 256) {
+        const int kk = e / M, i = e - kk * M;
+        const long long col = gather ? (long long)gather[k0 + kk] : (long long)(k0 + kk);
+        sA[i][kk] = gA[i + col * tk.lda];
+    }
+    for (int e = tid; e < (4 - M) * kn; e += 256) sA[M + e / kn][e % kn] = 0.0;
+    __syncthreads();      // also orders the reads of A before the in-place writes of a BETA0 task
     if (!B_KMAJ) {
         const int j = tr.tj * 256 + tid;
-        const bool live = j < tk.N;
+        if (j >= tk.N) return;
+        const double *bp = gB + j + (long long)k0 * tk.ldb;
         double acc[4] = {0.0, 0.0, 0.0, 0.0};
-        for (int kk = k0; kk < k1; kk++) {
-            const double bv = live ? gB[j + (long long)kk * tk.ldb] : 0.0;
-            const long long col = gather ? (long long)gather[kk] : (long long)kk;
+        int kk = 0;
+        for (; kk + 8 <= kn; kk += 8) {
+            double bv[8];
 #pragma unroll
-            for (int i = 0; i < 4; i++)
-                if (i < M) acc[i] += gA[i + col * tk.lda] * bv;
-        }
-        if (beta0) __syncthreads();          // in-place tasks (C aliases A): all reads precede all writes
-        if (live) {
-            const long long ccol = scat ? (long long)scat[j] : (long long)j;
+            for (int u = 0; u < 8; u++) bv[u] = bp[(long long)(kk + u) * tk.ldb];
 #pragma unroll
-            for (int i = 0; i < 4; i++)
-                if (i < M) {
-                    const double v = neg ? -acc[i] : acc[i];
-                    double *p = gC + i + ccol * tk.ldc;
-                    if (beta0) *p = v; else atomicAdd(p, v);
-                }
+            for (int u = 0; u < 8; u++)
+#pragma unroll
+                for (int i = 0; i < 4; i++) acc[i] += sA[i][kk + u] * bv[u];
         }
+        for (; kk < kn; kk++) {
+            const double bv = bp[(long long)kk * tk.ldb];
+#pragma unroll
+            for (int i = 0; i < 4; i++) acc[i] += sA[i][kk] * bv;
+        }
+        const long long ccol = scat ? (long long)scat[j] : (long long)j;
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+            if (i < M) {
+                const double v = neg ? -acc[i] : acc[i];
+                double *p = gC + i + ccol * tk.ldc;
+                if (beta0) *p = v; else atomicAdd(p, v);
+            }
     } else {
         const int w = tid >> 5, lane = tid & 31;
-        double res[8][4];
-#pragma unroll
+#pragma unroll 1
         for (int c = 0; c < 8; c++) {
             const int j = tr.tj * 64 + w * 8 + c;
+            if (j >= tk.N) break;
+            const double *bp = gB + k0 + (long long)j * tk.ldb;
             double acc[4] = {0.0, 0.0, 0.0, 0.0};
-            if (j < tk.N) {
-                for (int kk = k0 + lane; kk < k1; kk += 32) {
-                    const double bv = gB[kk + (long long)j * tk.ldb];
-                    const long long col = gather ? (long long)gather[kk] : (long long)kk;
+            int kk = lane;
+            for (; kk + 96 < kn; kk += 128) {
+                double bv[4];
 #pragma unroll
-                    for (int i = 0; i < 4; i++)
-                        if (i < M) acc[i] += gA[i + col * tk.lda] * bv;
-                }
+                for (int u = 0; u < 4; u++) bv[u] = bp[kk + 32 * u];
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+#pragma unroll
+                    for (int i = 0; i < 4; i++) acc[i] += sA[i][kk + 32 * u] * bv[u];
+            }
+            for (; kk < kn; kk += 32) {
+                const double bv = bp[kk];
+#pragma unroll
+                for (int i = 0; i < 4; i++) acc[i] += sA[i][kk] * bv;
             }
 #pragma unroll
-            for (int i = 0; i < 4; i++) {
-                double s = acc[i];
-                for (int o = 16; o; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
-                res[c][i] = s;
-            }
-        }
-        if (beta0) __syncthreads();
-        if (lane == 0) {
-#pragma unroll
-            for (int c = 0; c < 8; c++) {
-                const int j = tr.tj * 64 + w * 8 + c;
-                if (j >= tk.N) continue;
+            for (int i = 0; i < 4; i++)
+                for (int o = 16; o; o >>= 1) acc[i] += __shfl_down_sync(0xffffffffu, acc[i], o);
+            if (lane == 0) {
                 const long long ccol = scat ? (long long)scat[j] : (long long)j;
 #pragma unroll
                 for (int i = 0; i < 4; i++)
                     if (i < M) {
-                        const double v = neg ? -res[c][i] : res[c][i];
+                        const double v = neg ? -acc[i] : acc[i];
                         double *p = gC + i + ccol * tk.ldc;
                         if (beta0) *p = v; else atomicAdd(p, v);
                     }

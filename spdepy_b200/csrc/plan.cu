@@ -89,14 +89,25 @@ __global__ void __launch_bounds__(256) k_potrf(const PotrfTask *__restrict__ tas
         for (int j = 0; j < b; j++) {
             const double d = a[j][j];
             const bool ok = d > 0.0;
-            const double ljj = ok ? sqrt(d) : nan("");
-            const double inv = 1.0 / ljj;
-            const double li = (i > j && i < b) ? a[i][j] * inv : 0.0;
-            if (i > j && i < b)
-                for (int c = j + 1 + ty; c <= i; c += 4) a[i][c] -= li * (a[c][j] * inv);
+            const double inv = ok ? rsqrt(d) : nan("");     // 1/l_jj; l_jj = d * inv
+            const bool mine = i > j && i < b;
+            const double li = mine ? a[i][j] * inv : 0.0;
+            if (mine) {
+                // a[i][c] -= l_ic * l_cj for my quarter of the columns, four independent updates in flight
+                int c = j + 1 + ty;
+                for (; c + 12 <= i; c += 16) {
+                    const double p0 = a[c][j], p1 = a[c + 4][j], p2 = a[c + 8][j], p3 = a[c + 12][j];
+                    const double t0 = a[i][c], t1 = a[i][c + 4], t2 = a[i][c + 8], t3 = a[i][c + 12];
+                    a[i][c] = t0 - li * (p0 * inv);
+                    a[i][c + 4] = t1 - li * (p1 * inv);
+                    a[i][c + 8] = t2 - li * (p2 * inv);
+                    a[i][c + 12] = t3 - li * (p3 * inv);
+                }
+                for (; c <= i; c += 4) a[i][c] -= li * (a[c][j] * inv);
+            }
             __syncthreads();                       // column j has been read by everyone
-            if (ty == 0 && i > j && i < b) a[i][j] = li;
-            if (tid == 0) { a[j][j] = ljj; if (!ok && bad < 0) bad = j; }
+            if (ty == 0 && mine) a[i][j] = li;
+            if (tid == 0) { a[j][j] = d * inv; if (!ok && bad < 0) bad = j; }
         }
         __syncthreads();
     }
@@ -106,15 +117,16 @@ __global__ void __launch_bounds__(256) k_potrf(const PotrfTask *__restrict__ tas
     {
         const int c = tid >> 2, l = tid & 3;
         const bool live = c < b;
-        const double wcc = live ? 1.0 / a[c][c] : 0.0;
-        if (live && l == 0) wd[c] = wcc;
+        if (tid < NB) wd[tid] = tid < b ? 1.0 / a[tid][tid] : 0.0;
+        __syncthreads();
+        const double wcc = live ? wd[c] : 0.0;
         for (int i = 1; i < NB; i++) {
             double s = 0.0;
             if (live && i > c && i < b)
                 for (int k = c + 1 + l; k < i; k += 4) s += a[i][k] * a[c][k];
             s += __shfl_xor_sync(0xffffffffu, s, 1);
             s += __shfl_xor_sync(0xffffffffu, s, 2);
-            if (live && l == 0 && i > c && i < b) a[c][i] = (-a[i][c] * wcc - s) / a[i][i];
+            if (live && l == 0 && i > c && i < b) a[c][i] = (-a[i][c] * wcc - s) * wd[i];
             __syncwarp();
         }
     }

@@ -11,7 +11,7 @@
 namespace spde {
 
 constexpr int NB = 64;        // diagonal-block size of the dense partial Cholesky
-constexpr int OUTER = 4;      // inner blocks per outer (right-looking) block -> 256 columns
+constexpr int OUTER = 8;      // inner blocks per outer (right-looking) block -> 512 columns
 
 struct SNode {
     int first, nc, nr, ncp, ld, nblk, depth, parent, ldu;

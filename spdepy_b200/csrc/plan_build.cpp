@@ -584,7 +584,7 @@ void Plan::build_selinv_program()
                     else B.join_gemm(q, t);
                 }
                 // Z_pp -= Y^T Z[below,p]   (split over K, accumulated atomically)
-                const int chunk = 2048;
+                const int chunk = 512;
                 bool opened = false;
                 for (int k0 = 0; k0 < mb; k0 += chunk) {
                     GemmTask u = B.task(SP_Y, Y + k0, ldy, sp_z, F + (r0 + k0) + (int64_t)c0 * x.ld, x.ld,

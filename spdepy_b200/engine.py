@@ -251,6 +251,12 @@ class Engine:
                                         ptr(GQ0), _stream()))
         return GA, Gq, GQ0
 
+    def stencil_adjoint(self, hx, hy, GA: torch.Tensor, want_H: bool, G=None):
+        GH = torch.empty(8 * self.Ns, dtype=F64, device=_dev()) if want_H else None
+        GdG = torch.empty(self.Ns, 4, dtype=F64, device=_dev()) if G is not None else None
+        check(lib.spde_stencil_adjoint(self.M, self.N, self.bc, hx, hy, ptr(GA), ptr(GH), ptr(G), ptr(GdG), _stream()))
+        return GH, GdG
+
     @staticmethod
     def gemv_t(B: torch.Tensor, u: torch.Tensor) -> torch.Tensor:
         out = torch.empty(B.shape[1], dtype=F64, device=_dev())

@@ -205,9 +205,11 @@ class SPDE2D:
             return H, dirs
         gam = np.exp(g.evalBH(par=p["gamma"]))                      # (Ns, 4)
         H = I2 * (np.stack([gam, gam], axis=2))[:, :, :, None]
+        self._face_fields = {"gam": gam}
         if self.Hkind == "aniso":
             vv = np.stack([g.evalBH(p["vx"]), g.evalBH(p["vy"])], axis=2)
             H = H + vv[:, :, :, None] * vv[:, :, None, :]
+            self._face_fields.update(vx=vv[:, :, 0], vy=vv[:, :, 1])
         elif self.Hkind == "ha":
             raise NotImplementedError("spatially varying half-angle diffusion: next round (SURVEY.md section 8f)")
         if want_dirs:
@@ -234,6 +236,8 @@ class SPDE2D:
         kap = np.exp(g.evalB(par=p["kappa"])) if self.kvar else np.exp(p["kappa"][:1])
         H, _ = self._H_and_dirs(p, want_dirs=False)
         st = {"par": par, "p": p, "V": V, "dt": dt, "kappa": to_dev(kap), "H": H}
+        if self.Hvar:
+            st["faces"] = {k: to_dev(np.ascontiguousarray(v)) for k, v in self._face_fields.items()}
         ah = eng.ah_stencil(g.hx, g.hy, to_dev(H), self.Hvar)
         aw = None
         if self.wkind == "const":
@@ -326,24 +330,39 @@ class SPDE2D:
         else:
             out.append(Engine.dot(u.contiguous(), torch.ones_like(u)))
         # diffusion
-        _, dirs = self._H_and_dirs(st["p"], want_dirs=True)
         sgn = -dt if self.timed else -1.0
-        for dH in dirs:
-            ah = eng.ah_stencil(g.hx, g.hy, to_dev(dH), self.Hvar)
-            out.append(sgn * Engine.dot(GA, ah))
+        wsd = to_dev(st["ws"]) if self.wkind is not None else None
+        if self.Hvar:
+            # spline fields: adjoint of the face stencil, then one GEMV with the face basis per parameter block
+            GH, GdG = eng.stencil_adjoint(g.hx, g.hy, GA, True, wsd if self.wkind == "var" else None)
+            GH = GH.view(8, Ns)
+            f = st["faces"]
+            D = torch.stack([GH[0], GH[1], GH[6], GH[7]], dim=1)        # dS/d(H00 at W,E), d(H11 at S,N)
+            bsH = self._bsH_dev()
+            out.extend(to_host(sgn * eng.gemv_t(bsH, (f["gam"] * D).reshape(-1).contiguous())).tolist())
+            if self.Hkind == "aniso":
+                O = torch.stack([GH[2], GH[3], GH[4], GH[5]], dim=1)    # dS/d(H10 at W,E), d(H01 at S,N)
+                vx, vy = f["vx"], f["vy"]
+                u_vx = torch.cat([2 * vx[:, :2] * D[:, :2] + vy[:, :2] * O[:, :2], vy[:, 2:] * O[:, 2:]], dim=1)
+                u_vy = torch.cat([vx[:, :2] * O[:, :2], vx[:, 2:] * O[:, 2:] + 2 * vy[:, 2:] * D[:, 2:]], dim=1)
+                out.extend(to_host(sgn * eng.gemv_t(bsH, u_vx.reshape(-1).contiguous())).tolist())
+                out.extend(to_host(sgn * eng.gemv_t(bsH, u_vy.reshape(-1).contiguous())).tolist())
+        else:
+            GdG = None
+            _, dirs = self._H_and_dirs(st["p"], want_dirs=True)
+            for dH in dirs:
+                ah = eng.ah_stencil(g.hx, g.hy, to_dev(dH), self.Hvar)
+                out.append(sgn * Engine.dot(GA, ah))
         # advection
         if self.wkind == "const":
-            wsd = to_dev(st["ws"])
             for d in (1, 2):
                 out.append(dt * Engine.dot(GA, eng.aw_stencil(g.hx, g.hy, wsd, None, False, d, False)))
         elif self.wkind == "var":
-            wsd = to_dev(st["ws"])
-            for i in range(2 * self.Np):
-                dpar = np.zeros(2 * self.Np)
-                dpar[i] = 1
-                dws = to_dev(np.ascontiguousarray(g.evalAdv(dpar)))
-                aw = eng.aw_stencil(g.hx, g.hy, wsd, dws, True, 1 if i < self.Np else 2, True)
-                out.append(dt * Engine.dot(GA, aw))
+            if GdG is None:
+                _, GdG = eng.stencil_adjoint(g.hx, g.hy, GA, False, wsd)
+            BAx, BAy = self._bsA_dev()
+            out.extend(to_host(dt * eng.gemv_t(BAx, GdG[:, [0, 2]].reshape(-1).contiguous())).tolist())
+            out.extend(to_host(dt * eng.gemv_t(BAy, GdG[:, [1, 3]].reshape(-1).contiguous())).tolist())
         if self.timed:
             # log sigma: dQ = -(Q - blockdiag(Q0-part))   (advection_diffusion2D.py:170-175)
             s_total = Engine.dot(W, st["Q"])
@@ -352,6 +371,20 @@ class SPDE2D:
             if st["joint"]:
                 out.extend(self.mod0._grad_from_weights(st["mod0"], GQ0))
         return out
+
+    def _bsH_dev(self):
+        if getattr(self, "_bsH_cache", None) is None:
+            self._bsH_cache = to_dev(np.ascontiguousarray(self.grid.bsH.reshape(-1, self.Np)))
+        return self._bsH_cache
+
+    def _bsA_dev(self):
+        """Effective advection bases: d evalAdv / d theta_i = advBound(bsA[:, f, i]) (spat2Dtemp_regular_mesh.py:267-275)."""
+        if getattr(self, "_bsA_cache", None) is None:
+            g = self.grid
+            B = g.advBound(g.bsA.reshape(g.bsA.shape[0], -1)).reshape(-1, 4, self.Np)
+            self._bsA_cache = (to_dev(np.ascontiguousarray(B[:, [0, 2], :].reshape(-1, self.Np))),
+                               to_dev(np.ascontiguousarray(B[:, [1, 3], :].reshape(-1, self.Np))))
+        return self._bsA_cache
 
     def _bs_dev(self):
         if getattr(self, "_bs_cache", None) is None:

@@ -58,3 +58,28 @@ for prog, pname in ((0, "factor"), (3, "selinv")):
     for k, v in other:
         agg[k] = agg.get(k, 0.0) + float(v)
     print("   non-gemm ms:", {k: round(v, 2) for k, v in agg.items()})
+
+# --- triangular solves with one right-hand side (conditional mean)
+eng = m.engine
+x = torch.randn(eng.n, 1, dtype=torch.float64, device="cuda")
+eng.solve(1, x.clone())
+plan.profile(True)
+eng.solve(1, x.clone())
+torch.cuda.synchronize()
+pms, pcnt = plan.profile(False)
+print("\n## solve_A k=1: per kind ms", {k: round(float(pms[i].sum()), 3) for i, k in enumerate(kinds + ["gemv"])},
+      "launches", {k: int(pcnt[i].sum()) for i, k in enumerate(kinds + ["gemv"])})
+for prog, pname in ((1, "forward"), (2, "backward")):
+    P = pe.Program(plan, prog, 1)
+    ms = plan.export(prog, 7, "f4", 1)
+    order = np.argsort(-ms)[:8]
+    print("  %s: %d launches, %.2f ms; slowest:" % (pname, len(ms), ms.sum()),
+          [(round(float(ms[i]), 3), int(P.launches[i]["kind"]), int(P.launches[i]["ntiles"]), int(P.launches[i]["ntasks"])) for i in order])
+t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+for _ in range(3):
+    eng.solve(1, x.clone())
+torch.cuda.synchronize(); t0.record()
+for _ in range(5):
+    eng.solve(1, x.clone())
+t1.record(); torch.cuda.synchronize()
+print("  graph-replayed solve_A k=1: %.2f ms" % (t0.elapsed_time(t1) / 5))
