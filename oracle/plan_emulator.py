@@ -89,8 +89,9 @@ class Emulator:
             if gemv:
                 assert M <= 4
                 i0, j0 = 0, int(tr["tj"]) * BN
-                ka, kb = int(tr["ti"]) * 1024, min(K, int(tr["ti"]) * 1024 + 1024)
-                assert not (f & GF_BETA0) or K <= 1024
+                kc = 1024 if bk else 256
+                ka, kb = int(tr["ti"]) * kc, min(K, int(tr["ti"]) * kc + kc)
+                assert not (f & GF_BETA0) or K <= kc
             else:
                 i0, j0 = int(tr["ti"]) * BM, int(tr["tj"]) * BN
                 ka, kb = 0, K

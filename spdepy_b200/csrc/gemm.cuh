@@ -265,17 +265,19 @@ k_gemm_grouped(const GemmTask *__restrict__ tasks, const TileRef *__restrict__ t
 // split across CTAs (atomic accumulation) so that a single wide front still fills the machine.
 //   B_KMAJ=false: B(j,kk) at b + j + kk*ldb -> one thread per output column j (256 columns per tile)
 //   B_KMAJ=true : B(j,kk) at b + kk + j*ldb -> one warp per output column, lanes stride over kk (64 columns per tile)
-constexpr int GEMV_KC = 1024;
+constexpr int GEMV_KC_N = 256;     // K chunk of the N-contiguous variant (one thread per column)
+constexpr int GEMV_KC_K = 1024;    // K chunk of the K-contiguous variant (one warp per 8 columns)
 
 template <bool B_KMAJ>
 __global__ void __launch_bounds__(256) k_gemv_grouped(const GemmTask *__restrict__ tasks, const TileRef *__restrict__ tiles,
                                                       GemmSpaces sp)
 {
-    __shared__ double sA[4][GEMV_KC];        // the right-hand-side slice of this K chunk (<= 4 columns)
+    constexpr int KC = B_KMAJ ? GEMV_KC_K : GEMV_KC_N;
+    __shared__ double sA[4][KC];             // the right-hand-side slice of this K chunk (<= 4 columns)
     const TileRef tr = tiles[blockIdx.x];
     const GemmTask tk = tasks[tr.task];
     const int tid = threadIdx.x;
-    const int k0 = tr.ti * GEMV_KC, kn = min(tk.K, k0 + GEMV_KC) - k0;
+    const int k0 = tr.ti * KC, kn = min(tk.K, k0 + KC) - k0;
     const double *gA = sp.base[tk.flags & 7] + tk.a;
     const double *gB = sp.base[(tk.flags >> 3) & 7] + tk.b;
     double *gC = sp.base[(tk.flags >> 6) & 7] + tk.c;
@@ -283,12 +285,15 @@ __global__ void __launch_bounds__(256) k_gemv_grouped(const GemmTask *__restrict
     const int *scat = (tk.flags & GF_SCATTER_C) ? sp.idx + tk.cidx : nullptr;
     const bool neg = tk.flags & GF_NEG, beta0 = tk.flags & GF_BETA0;
     const int M = tk.M;
-    for (int e = tid; e < kn * M; e += 256) {
-        const int kk = e / M, i = e - kk * M;
-        const long long col = gather ? (long long)gather[k0 + kk] : (long long)(k0 + kk);
-        sA[i][kk] = gA[i + col * tk.lda];
+    for (int e = tid; e < 4 * KC; e += 256) {
+        const int i = e / KC, kk = e - i * KC;
+        double v = 0.0;
+        if (i < M && kk < kn) {
+            const long long col = gather ? (long long)gather[k0 + kk] : (long long)(k0 + kk);
+            v = gA[i + col * tk.lda];
+        }
+        sA[i][kk] = v;
     }
-    for (int e = tid; e < (4 - M) * kn; e += 256) sA[M + e / kn][e % kn] = 0.0;
     __syncthreads();      // also orders the reads of A before the in-place writes of a BETA0 task
     if (!B_KMAJ) {
         const int j = tr.tj * 256 + tid;
@@ -296,12 +301,12 @@ __global__ void __launch_bounds__(256) k_gemv_grouped(const GemmTask *__restrict
         const double *bp = gB + j + (long long)k0 * tk.ldb;
         double acc[4] = {0.0, 0.0, 0.0, 0.0};
         int kk = 0;
-        for (; kk + 8 <= kn; kk += 8) {
-            double bv[8];
+        for (; kk + 16 <= kn; kk += 16) {
+            double bv[16];
 #pragma unroll
-            for (int u = 0; u < 8; u++) bv[u] = bp[(long long)(kk + u) * tk.ldb];
+            for (int u = 0; u < 16; u++) bv[u] = bp[(long long)(kk + u) * tk.ldb];
 #pragma unroll
-            for (int u = 0; u < 8; u++)
+            for (int u = 0; u < 16; u++)
 #pragma unroll
                 for (int i = 0; i < 4; i++) acc[i] += sA[i][kk + u] * bv[u];
         }
@@ -319,37 +324,48 @@ __global__ void __launch_bounds__(256) k_gemv_grouped(const GemmTask *__restrict
                 if (beta0) *p = v; else atomicAdd(p, v);
             }
     } else {
+        // eight columns per warp, all in flight together: 8 (x2) independent coalesced loads per lane
         const int w = tid >> 5, lane = tid & 31;
-#pragma unroll 1
-        for (int c = 0; c < 8; c++) {
-            const int j = tr.tj * 64 + w * 8 + c;
-            if (j >= tk.N) break;
-            const double *bp = gB + k0 + (long long)j * tk.ldb;
-            double acc[4] = {0.0, 0.0, 0.0, 0.0};
-            int kk = lane;
-            for (; kk + 96 < kn; kk += 128) {
-                double bv[4];
+        const int jb = tr.tj * 64 + w * 8;
+        if (jb >= tk.N) return;
+        const int nc = min(8, tk.N - jb);
+        const double *bp = gB + k0 + (long long)jb * tk.ldb;
+        double acc[8][4];
 #pragma unroll
-                for (int u = 0; u < 4; u++) bv[u] = bp[kk + 32 * u];
+        for (int c = 0; c < 8; c++)
 #pragma unroll
-                for (int u = 0; u < 4; u++)
+            for (int i = 0; i < 4; i++) acc[c][i] = 0.0;
+        for (int kk = lane; kk < kn; kk += 64) {
+            double bv[8], bw[8];
+            const bool second = kk + 32 < kn;
 #pragma unroll
-                    for (int i = 0; i < 4; i++) acc[i] += sA[i][kk + 32 * u] * bv[u];
+            for (int c = 0; c < 8; c++) {
+                bv[c] = c < nc ? bp[kk + (long long)c * tk.ldb] : 0.0;
+                bw[c] = (second && c < nc) ? bp[kk + 32 + (long long)c * tk.ldb] : 0.0;
             }
-            for (; kk < kn; kk += 32) {
-                const double bv = bp[kk];
 #pragma unroll
-                for (int i = 0; i < 4; i++) acc[i] += sA[i][kk] * bv;
-            }
+            for (int c = 0; c < 8; c++)
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    acc[c][i] += sA[i][kk] * bv[c];
+                    if (second) acc[c][i] += sA[i][kk + 32] * bw[c];
+                }
+        }
+#pragma unroll
+        for (int c = 0; c < 8; c++)
 #pragma unroll
             for (int i = 0; i < 4; i++)
-                for (int o = 16; o; o >>= 1) acc[i] += __shfl_down_sync(0xffffffffu, acc[i], o);
-            if (lane == 0) {
+                for (int o = 16; o; o >>= 1) acc[c][i] += __shfl_down_sync(0xffffffffu, acc[c][i], o);
+        if (lane == 0) {
+#pragma unroll
+            for (int c = 0; c < 8; c++) {
+                if (c >= nc) break;
+                const int j = jb + c;
                 const long long ccol = scat ? (long long)scat[j] : (long long)j;
 #pragma unroll
                 for (int i = 0; i < 4; i++)
                     if (i < M) {
-                        const double v = neg ? -acc[i] : acc[i];
+                        const double v = neg ? -acc[c][i] : acc[c][i];
                         double *p = gC + i + ccol * tk.ldc;
                         if (beta0) *p = v; else atomicAdd(p, v);
                     }

@@ -196,7 +196,7 @@ struct LevelBuilder {
     }
     void emit_gemv_launch(int bk, const std::vector<const Step *> &steps)
     {
-        const int TN = bk ? 64 : 256, KC = 1024;
+        const int TN = bk ? 64 : 256, KC = bk ? GEMV_KC_K : GEMV_KC_N;
         Launch L;
         memset(&L, 0, sizeof L);
         L.kind = LK_GEMV;
