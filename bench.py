@@ -325,7 +325,7 @@ def run_ours(args):
                 "gemm_share_of_scheduled_time": gemm_ms / total_ms if total_ms else None,
                 "algorithmic_flops_per_step": alg_flops,
                 "by_kind_ms": {k: float(pms[i].sum()) for i, k in enumerate(
-                    ["gemm", "potrf", "extend_add", "memset", "gather", "wtw", "extract"])}}
+                    ["gemm", "potrf", "extend_add", "memset", "gather", "wtw", "extract", "gemv"])}}
         # Cholesky GFLOP/s = sum_j cc_j^2 / t_factor (BASELINE.json metric, CHOLMOD's flop convention)
         Qdev = m._state["Q"]
         m.engine.factorize(0, Qdev)

@@ -125,6 +125,11 @@ int spde_plan_profile(spde_plan *p, int enable, double *h_out, int reset);
  * the original ordering are read, as CHOLMOD does); d_cnt (n doubles, may be NULL) is the diagonal
  * of S^T S (advection_diffusion2D.py:192).  `which` selects one of two factor stores (0: Q, 1: Q_c). */
 int spde_factorize(spde_plan *p, int which, const double *d_Q, const double *d_cnt, double tau, void *stream);
+/* Asynchronous form: spde_factorize_async enqueues the schedule (on a private stream per store once its CUDA
+ * graph exists) and returns; spde_factor_wait orders it before `stream`, synchronises and returns the status.
+ * Issuing both stores back to back lets the two factorisations of logLike overlap. */
+int spde_factorize_async(spde_plan *p, int which, const double *d_Q, const double *d_cnt, double tau, void *stream);
+int spde_factor_wait(spde_plan *p, int which, void *stream);
 int spde_factor_info(spde_plan *p, int which, int *h_status, int *h_bad_column);
 int spde_logdet(spde_plan *p, int which, double *h_logdet, void *stream);
 
@@ -139,6 +144,9 @@ int spde_solve(spde_plan *p, int which, int mode, double *d_X, int k, void *stre
 /* Takahashi recursion on the supernodal structure; writes Z = (L L^T)^-1 restricted to the
  * pattern of Q into d_Zq (same Q25/Q43 layout, all stored slots filled symmetrically). */
 int spde_selinv(spde_plan *p, int which, double *d_Zq, void *stream);
+/* split form (start both stores, then fetch both) so the two Takahashi passes overlap */
+int spde_selinv_start(spde_plan *p, int which, void *stream);
+int spde_selinv_fetch(spde_plan *p, int which, double *d_Zq, void *stream);
 
 /* ------------------------------------------------------------------ likelihood / gradient reductions (K8,K9,K11) */
 /* y = Q x for k right-hand sides (x, y row-major n x k): stencil apply, no index arrays. */

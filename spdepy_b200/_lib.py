@@ -52,10 +52,14 @@ _SIGS = {
     "spde_plan_export": (c_int, [c_vp, c_int, c_int, c_int, c_vp, ctypes.POINTER(c_i64), ctypes.POINTER(c_int)]),
     "spde_plan_profile": (c_int, [c_vp, c_int, c_vp, c_int]),
     "spde_factorize": (c_int, [c_vp, c_int, c_vp, c_vp, c_dbl, c_vp]),
+    "spde_factorize_async": (c_int, [c_vp, c_int, c_vp, c_vp, c_dbl, c_vp]),
+    "spde_factor_wait": (c_int, [c_vp, c_int, c_vp]),
     "spde_factor_info": (c_int, [c_vp, c_int, ctypes.POINTER(c_int), ctypes.POINTER(c_int)]),
     "spde_logdet": (c_int, [c_vp, c_int, ctypes.POINTER(c_dbl), c_vp]),
     "spde_solve": (c_int, [c_vp, c_int, c_int, c_vp, c_int, c_vp]),
     "spde_selinv": (c_int, [c_vp, c_int, c_vp, c_vp]),
+    "spde_selinv_start": (c_int, [c_vp, c_int, c_vp]),
+    "spde_selinv_fetch": (c_int, [c_vp, c_int, c_vp, c_vp]),
     "spde_q_apply": (c_int, [c_int, c_int, c_int, c_int, c_vp, c_vp, c_int, c_vp, c_vp]),
     "spde_dot": (c_int, [c_vp, c_vp, c_i64, ctypes.POINTER(c_dbl), c_vp]),
     "spde_wdot": (c_int, [c_vp, c_vp, c_vp, c_i64, c_int, ctypes.POINTER(c_dbl), c_vp]),

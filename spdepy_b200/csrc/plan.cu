@@ -310,13 +310,13 @@ static GemmSpaces spaces_of(Plan &p, int which)
 {
     GemmSpaces sp;
     sp.base[0] = p.d_L[which];
-    sp.base[1] = p.d_arena[0];
-    sp.base[2] = p.d_arena[1];
+    sp.base[1] = p.d_arena[which][0];
+    sp.base[2] = p.d_arena[which][1];
     sp.base[3] = p.d_dinv[which];
     sp.base[4] = p.d_X;
-    sp.base[5] = p.d_ybuf;
-    sp.base[6] = p.d_zarena[0];
-    sp.base[7] = p.d_zarena[1];
+    sp.base[5] = p.d_ybuf[which];
+    sp.base[6] = p.d_zarena[which][0];
+    sp.base[7] = p.d_zarena[which][1];
     sp.idx = p.d_idx;
     return sp;
 }
@@ -343,7 +343,7 @@ static int issue_program(Plan &p, Program &P, int which, cudaStream_t st, double
             else k_gemv_grouped<false><<<L.ntiles, 256, 0, st>>>(P.d_gemm + L.task0, P.d_tiles + L.tile0, sp);
             break;
         case LK_POTRF:
-            k_potrf<<<L.ntasks, 256, 0, st>>>(P.d_potrf + L.task0, p.d_L[which], p.d_dinv[which], p.d_status);
+            k_potrf<<<L.ntasks, 256, 0, st>>>(P.d_potrf + L.task0, p.d_L[which], p.d_dinv[which], p.d_status + which);
             break;
         case LK_EXTADD:
             k_extend_add<<<L.ntiles, dim3(32, 8), 0, st>>>(P.d_ext + L.task0, P.d_tiles + L.tile0, sp);
@@ -401,8 +401,20 @@ static void init_gemm_attributes()
 // Run a schedule: first call plainly, second call captured into a CUDA graph, later calls replayed.  The
 // schedules are static per mesh (fixed task lists, fixed workspace pointers), so replay removes the host
 // cost of thousands of launches per evaluation.
-static int run_program(Plan &p, Program &P, int which, cudaStream_t st, double *d_Zq)
+// make the caller's stream wait for the in-flight graph of a factor store
+static int join_store(Plan &p, int which, cudaStream_t st)
 {
+    if (p.pending[which]) {
+        SPDE_CUDA_CHECK(cudaStreamWaitEvent(st, p.ev_out[which], 0));
+        p.pending[which] = false;
+    }
+    return SPDE_OK;
+}
+
+static int run_program(Plan &p, Program &P, int which, cudaStream_t st, double *d_Zq, bool defer_join = false)
+{
+    int rc = join_store(p, which, st);
+    if (rc) return rc;
     if (p.prof_on || !p.use_graphs) return issue_program(p, P, which, st, d_Zq);
     GemmSpaces sp = spaces_of(p, which);
     unsigned long long key = 1469598103934665603ull;
@@ -412,34 +424,35 @@ static int run_program(Plan &p, Program &P, int which, cudaStream_t st, double *
         cudaGraphExecDestroy(P.graph[which]);
         P.graph[which] = nullptr;
     }
+    if (!p.cap_stream[which]) {
+        SPDE_CUDA_CHECK(cudaStreamCreateWithFlags(&p.cap_stream[which], cudaStreamNonBlocking));
+        SPDE_CUDA_CHECK(cudaEventCreateWithFlags(&p.ev_in[which], cudaEventDisableTiming));
+        SPDE_CUDA_CHECK(cudaEventCreateWithFlags(&p.ev_out[which], cudaEventDisableTiming));
+    }
+    cudaStream_t cs = p.cap_stream[which];
     if (!P.graph[which]) {
         if (P.runs[which]++ == 0) return issue_program(p, P, which, st, d_Zq);   // warm run: uploads, lazy init
-        if (!p.cap_stream) {
-            SPDE_CUDA_CHECK(cudaStreamCreateWithFlags(&p.cap_stream, cudaStreamNonBlocking));
-            SPDE_CUDA_CHECK(cudaEventCreateWithFlags(&p.ev_in, cudaEventDisableTiming));
-            SPDE_CUDA_CHECK(cudaEventCreateWithFlags(&p.ev_out, cudaEventDisableTiming));
-        }
-        SPDE_CUDA_CHECK(cudaStreamBeginCapture(p.cap_stream, cudaStreamCaptureModeRelaxed));
+        SPDE_CUDA_CHECK(cudaStreamBeginCapture(cs, cudaStreamCaptureModeRelaxed));
         const long long before = spde_launch_count(0);
-        int rc = issue_program(p, P, which, p.cap_stream, d_Zq);
+        rc = issue_program(p, P, which, cs, d_Zq);
         count_launch((int)(before - spde_launch_count(0)));     // counted again at every replay
         cudaGraph_t g = nullptr;
-        cudaError_t e = cudaStreamEndCapture(p.cap_stream, &g);
+        cudaError_t e = cudaStreamEndCapture(cs, &g);
         if (rc) { if (g) cudaGraphDestroy(g); return rc; }
         SPDE_CUDA_CHECK(e);
         SPDE_CUDA_CHECK(cudaGraphInstantiate(&P.graph[which], g, 0));
         cudaGraphDestroy(g);
         P.graph_key[which] = key;
     }
-    SPDE_CUDA_CHECK(cudaEventRecord(p.ev_in, st));
-    SPDE_CUDA_CHECK(cudaStreamWaitEvent(p.cap_stream, p.ev_in, 0));
-    SPDE_CUDA_CHECK(cudaGraphLaunch(P.graph[which], p.cap_stream));
-    SPDE_CUDA_CHECK(cudaEventRecord(p.ev_out, p.cap_stream));
-    SPDE_CUDA_CHECK(cudaStreamWaitEvent(st, p.ev_out, 0));
+    SPDE_CUDA_CHECK(cudaEventRecord(p.ev_in[which], st));
+    SPDE_CUDA_CHECK(cudaStreamWaitEvent(cs, p.ev_in[which], 0));
+    SPDE_CUDA_CHECK(cudaGraphLaunch(P.graph[which], cs));
+    SPDE_CUDA_CHECK(cudaEventRecord(p.ev_out[which], cs));
+    p.pending[which] = true;
     int nk = 0;
     for (const Launch &L : P.launches) nk += L.kind != LK_ZERO;
     count_launch(nk);
-    return SPDE_OK;
+    return defer_join ? SPDE_OK : join_store(p, which, st);
 }
 
 static int ensure_device(Plan &p, int which)
@@ -457,13 +470,13 @@ static int ensure_device(Plan &p, int which)
         SPDE_CUDA_CHECK(upload(p.diagpos, &p.d_diagpos));
         SPDE_CUDA_CHECK(upload(p.cand_slots, &p.d_cand));
         SPDE_CUDA_CHECK(upload(p.sym.perm, &p.d_perm));
-        SPDE_CUDA_CHECK(cudaMalloc((void **)&p.d_status, sizeof(int)));
+        SPDE_CUDA_CHECK(cudaMalloc((void **)&p.d_status, 2 * sizeof(int)));
         SPDE_CUDA_CHECK(cudaMalloc((void **)&p.d_red, 4096 * sizeof(double)));
-        for (int a = 0; a < 2; a++)
-            if (p.arena_size[a]) SPDE_CUDA_CHECK(cudaMalloc((void **)&p.d_arena[a], p.arena_size[a] * sizeof(double)));
         p.device_ready |= 1;
     }
     if (!p.d_L[which]) {
+        for (int a = 0; a < 2; a++)
+            if (p.arena_size[a]) SPDE_CUDA_CHECK(cudaMalloc((void **)&p.d_arena[which][a], p.arena_size[a] * sizeof(double)));
         SPDE_CUDA_CHECK(cudaMalloc((void **)&p.d_L[which], std::max<int64_t>(p.l_size, 2) * sizeof(double)));
         SPDE_CUDA_CHECK(cudaMalloc((void **)&p.d_dinv[which], std::max<int64_t>(p.dinv_size, 2) * sizeof(double)));
     }
@@ -501,10 +514,13 @@ extern "C" void spde_plan_destroy(spde_plan *pp)
 {
     if (!pp) return;
     Plan *p = reinterpret_cast<Plan *>(pp);
-    for (int a = 0; a < 2; a++) { cudaFree(p->d_L[a]); cudaFree(p->d_dinv[a]); cudaFree(p->d_arena[a]); cudaFree(p->d_zarena[a]); }
-    cudaFree(p->d_ybuf); cudaFree(p->d_X); cudaFree(p->d_red); cudaFree(p->d_idx); cudaFree(p->d_qdest);
-    cudaFree(p->d_zq); cudaFree(p->d_diagpos); cudaFree(p->d_cand); cudaFree(p->d_perm); cudaFree(p->d_status); cudaFree(p->d_zentries);
-    if (p->cap_stream) { cudaStreamDestroy(p->cap_stream); cudaEventDestroy(p->ev_in); cudaEventDestroy(p->ev_out); }
+    for (int a = 0; a < 2; a++) {
+        cudaFree(p->d_L[a]); cudaFree(p->d_dinv[a]); cudaFree(p->d_ybuf[a]); cudaFree(p->d_zq[a]);
+        for (int b = 0; b < 2; b++) { cudaFree(p->d_arena[a][b]); cudaFree(p->d_zarena[a][b]); }
+        if (p->cap_stream[a]) { cudaStreamDestroy(p->cap_stream[a]); cudaEventDestroy(p->ev_in[a]); cudaEventDestroy(p->ev_out[a]); }
+    }
+    cudaFree(p->d_X); cudaFree(p->d_red); cudaFree(p->d_idx); cudaFree(p->d_qdest);
+    cudaFree(p->d_diagpos); cudaFree(p->d_cand); cudaFree(p->d_perm); cudaFree(p->d_status); cudaFree(p->d_zentries);
     free_program(p->factor);
     free_program(p->selinv);
     for (auto &kv : p->solve) free_program(kv.second);
@@ -616,30 +632,50 @@ extern "C" int spde_plan_profile(spde_plan *pp, int enable, double *h_out /* 8*1
     return SPDE_OK;
 }
 
-extern "C" int spde_factorize(spde_plan *pp, int which, const double *d_Q, const double *d_cnt, double tau, void *stream)
+// Asynchronous numeric factorisation: returns as soon as the schedule is enqueued (on the store's private
+// stream once its CUDA graph exists), so the factorisations of Q and Q + tau S^T S overlap.  Completion,
+// ordering with the caller's stream and the positive-definiteness status come from spde_factor_wait.
+extern "C" int spde_factorize_async(spde_plan *pp, int which, const double *d_Q, const double *d_cnt, double tau, void *stream)
 {
     Plan &p = *reinterpret_cast<Plan *>(pp);
     if (which < 0 || which > 1) { set_error("spde_factorize: which must be 0 or 1"); return SPDE_ERR_ARG; }
     cudaStream_t st = (cudaStream_t)stream;
     int rc = ensure_device(p, which);
     if (rc) return rc;
+    rc = join_store(p, which, st);
+    if (rc) return rc;
     const int n = p.sym.n;
     SPDE_CUDA_CHECK(cudaMemsetAsync(p.d_L[which], 0, (size_t)p.l_size * sizeof(double), st));
-    SPDE_CUDA_CHECK(cudaMemsetAsync(p.d_status, 0, sizeof(int), st));
+    SPDE_CUDA_CHECK(cudaMemsetAsync(p.d_status + which, 0, sizeof(int), st));
     const int ncand = (int)p.cand_slots.size();
     count_launch();
     k_scatter_q<<<148 * 8, 256, 0, st>>>(d_Q, p.d_qdest, p.d_cand, ncand, n, p.sym.nslots / 2, d_cnt, tau, p.d_L[which]);
     SPDE_LAUNCH_CHECK();
-    rc = run_program(p, p.factor, which, st, nullptr);
+    p.factored[which] = true;
+    p.status[which] = SPDE_OK;
+    p.bad_col[which] = -1;
+    return run_program(p, p.factor, which, st, nullptr, true);
+}
+
+extern "C" int spde_factor_wait(spde_plan *pp, int which, void *stream)
+{
+    Plan &p = *reinterpret_cast<Plan *>(pp);
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = join_store(p, which, st);
     if (rc) return rc;
     int h = 0;
-    SPDE_CUDA_CHECK(cudaMemcpyAsync(&h, p.d_status, sizeof(int), cudaMemcpyDeviceToHost, st));
+    SPDE_CUDA_CHECK(cudaMemcpyAsync(&h, p.d_status + which, sizeof(int), cudaMemcpyDeviceToHost, st));
     SPDE_CUDA_CHECK(cudaStreamSynchronize(st));
-    p.factored[which] = true;
     p.status[which] = h ? SPDE_ERR_NOT_SPD : SPDE_OK;
     p.bad_col[which] = h - 1;
     if (h) { set_error("matrix is not positive definite (pivot " + std::to_string(h - 1) + " of the permuted matrix)"); return SPDE_ERR_NOT_SPD; }
     return SPDE_OK;
+}
+
+extern "C" int spde_factorize(spde_plan *pp, int which, const double *d_Q, const double *d_cnt, double tau, void *stream)
+{
+    int rc = spde_factorize_async(pp, which, d_Q, d_cnt, tau, stream);
+    return rc ? rc : spde_factor_wait(pp, which, stream);
 }
 
 extern "C" int spde_factor_info(spde_plan *pp, int which, int *h_status, int *h_bad_column)
@@ -655,6 +691,7 @@ extern "C" int spde_logdet(spde_plan *pp, int which, double *h_logdet, void *str
     Plan &p = *reinterpret_cast<Plan *>(pp);
     if (!p.factored[which]) { set_error("spde_logdet: not factorised"); return SPDE_ERR_ARG; }
     cudaStream_t st = (cudaStream_t)stream;
+    { int rcj = join_store(p, which, st); if (rcj) return rcj; }
     const int nb = 1024;
     count_launch(2);
     k_logdet_partial<<<nb, 256, 0, st>>>(p.d_L[which], p.d_diagpos, p.sym.n, p.d_red);
@@ -670,6 +707,7 @@ extern "C" int spde_solve(spde_plan *pp, int which, int mode, double *d_X, int k
     Plan &p = *reinterpret_cast<Plan *>(pp);
     if (!p.factored[which] || k < 1 || mode < 1 || mode > 15 || !(mode & 3)) { set_error("spde_solve: bad state/arguments"); return SPDE_ERR_ARG; }
     cudaStream_t st = (cudaStream_t)stream;
+    { int rcj = join_store(p, which, st); if (rcj) return rcj; }
     const int n = p.sym.n, kp = k + (k & 1);
     const int64_t need = (int64_t)n * kp;
     if (p.x_cap < need) {
@@ -691,26 +729,43 @@ extern "C" int spde_solve(spde_plan *pp, int which, int mode, double *d_X, int k
     return SPDE_OK;
 }
 
-extern "C" int spde_selinv(spde_plan *pp, int which, double *d_Zq, void *stream)
+extern "C" int spde_selinv_start(spde_plan *pp, int which, void *stream)
 {
     Plan &p = *reinterpret_cast<Plan *>(pp);
     if (!p.factored[which]) { set_error("spde_selinv: not factorised"); return SPDE_ERR_ARG; }
     cudaStream_t st = (cudaStream_t)stream;
     p.build_selinv_program();
-    if (!(p.device_ready & 2)) {
-        for (int a = 0; a < 2; a++)
-            if (p.zarena_size[a]) SPDE_CUDA_CHECK(cudaMalloc((void **)&p.d_zarena[a], p.zarena_size[a] * sizeof(double)));
-        SPDE_CUDA_CHECK(cudaMalloc((void **)&p.d_ybuf, std::max<int64_t>(p.ybuf_size, 2) * sizeof(double)));
-        SPDE_CUDA_CHECK(upload(p.zentries, &p.d_zentries));
-        p.device_ready |= 2;
-    }
     const size_t zbytes = (size_t)p.sym.nslots * p.sym.n * sizeof(double);
-    if (!p.d_zq) SPDE_CUDA_CHECK(cudaMalloc((void **)&p.d_zq, zbytes));
-    SPDE_CUDA_CHECK(cudaMemsetAsync(p.d_zq, 0, zbytes, st));
-    int rc = run_program(p, p.selinv, which, st, p.d_zq);
+    if (!p.sel_ready[which]) {
+        for (int a = 0; a < 2; a++)
+            if (p.zarena_size[a]) SPDE_CUDA_CHECK(cudaMalloc((void **)&p.d_zarena[which][a], p.zarena_size[a] * sizeof(double)));
+        SPDE_CUDA_CHECK(cudaMalloc((void **)&p.d_ybuf[which], std::max<int64_t>(p.ybuf_size, 2) * sizeof(double)));
+        SPDE_CUDA_CHECK(cudaMalloc((void **)&p.d_zq[which], zbytes));
+        if (!p.d_zentries) SPDE_CUDA_CHECK(upload(p.zentries, &p.d_zentries));
+        p.sel_ready[which] = 1;
+    }
+    int rc = join_store(p, which, st);
     if (rc) return rc;
-    SPDE_CUDA_CHECK(cudaMemcpyAsync(d_Zq, p.d_zq, zbytes, cudaMemcpyDeviceToDevice, st));
+    SPDE_CUDA_CHECK(cudaMemsetAsync(p.d_zq[which], 0, zbytes, st));
+    return run_program(p, p.selinv, which, st, p.d_zq[which], true);
+}
+
+extern "C" int spde_selinv_fetch(spde_plan *pp, int which, double *d_Zq, void *stream)
+{
+    Plan &p = *reinterpret_cast<Plan *>(pp);
+    if (!p.sel_ready[which]) { set_error("spde_selinv_fetch: no selected inverse was started"); return SPDE_ERR_ARG; }
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = join_store(p, which, st);
+    if (rc) return rc;
+    const size_t zbytes = (size_t)p.sym.nslots * p.sym.n * sizeof(double);
+    SPDE_CUDA_CHECK(cudaMemcpyAsync(d_Zq, p.d_zq[which], zbytes, cudaMemcpyDeviceToDevice, st));
     return SPDE_OK;
+}
+
+extern "C" int spde_selinv(spde_plan *pp, int which, double *d_Zq, void *stream)
+{
+    int rc = spde_selinv_start(pp, which, stream);
+    return rc ? rc : spde_selinv_fetch(pp, which, d_Zq, stream);
 }
 
 // ---------------------------------------------------------------------------------------------

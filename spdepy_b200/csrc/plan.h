@@ -90,9 +90,11 @@ struct Plan {
     int device_ready = 0;
     double *d_L[2] = {nullptr, nullptr};
     double *d_dinv[2] = {nullptr, nullptr};
-    double *d_arena[2] = {nullptr, nullptr};
-    double *d_zarena[2] = {nullptr, nullptr};
-    double *d_ybuf = nullptr, *d_X = nullptr, *d_red = nullptr;
+    // per factor store (so the schedules of Q and Q + tau S^T S can run concurrently on two streams)
+    double *d_arena[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+    double *d_zarena[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+    double *d_ybuf[2] = {nullptr, nullptr};
+    double *d_X = nullptr, *d_red = nullptr;
     int64_t x_cap = 0;
     int *d_idx = nullptr;          // rows | relidx
     int64_t rel_base = 0;
@@ -104,9 +106,11 @@ struct Plan {
     // graph replay machinery: schedules are captured on a private stream and ordered against the caller's
     // stream with two events (the caller's stream may be the legacy default stream, which cannot capture)
     int use_graphs = 1;
-    cudaStream_t cap_stream = nullptr;
-    cudaEvent_t ev_in = nullptr, ev_out = nullptr;
-    double *d_zq = nullptr;
+    cudaStream_t cap_stream[2] = {nullptr, nullptr};
+    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
+    bool pending[2] = {false, false};   // a graph of this store is in flight and not yet joined with the caller's stream
+    double *d_zq[2] = {nullptr, nullptr};
+    int sel_ready[2] = {0, 0};
     // optional per-launch timing (CUDA events), accumulated per (launch kind, GEMM variant)
     bool prof_on = false;
     double prof_ms[8][16] = {{0}};

@@ -178,6 +178,25 @@ class Engine:
         check(lib.spde_factorize(self.plan.h, which, ptr(Q), ptr(cnt), float(tau), _stream()))
         return Factor(self, which)
 
+    def factorize_async(self, which: int, Q: torch.Tensor, cnt=None, tau: float = 0.0) -> None:
+        """Enqueue a factorisation without waiting; pair with :meth:`factor_wait` (lets Q and Q_c overlap)."""
+        self.serial[which] += 1
+        check(lib.spde_factorize_async(self.plan.h, which, ptr(Q), ptr(cnt), float(tau), _stream()))
+
+    def factor_wait(self, which: int) -> Factor:
+        check(lib.spde_factor_wait(self.plan.h, which, _stream()))
+        return Factor(self, which)
+
+    def selinv_pair(self):
+        """Takahashi selected inverse of both stores, the two schedules overlapping on their own streams."""
+        check(lib.spde_selinv_start(self.plan.h, 0, _stream()))
+        check(lib.spde_selinv_start(self.plan.h, 1, _stream()))
+        Z = torch.empty(self.nslots * self.n, dtype=F64, device=_dev())
+        Zc = torch.empty(self.nslots * self.n, dtype=F64, device=_dev())
+        check(lib.spde_selinv_fetch(self.plan.h, 0, ptr(Z), _stream()))
+        check(lib.spde_selinv_fetch(self.plan.h, 1, ptr(Zc), _stream()))
+        return Z, Zc
+
     def logdet(self, which: int) -> float:
         out = ctypes.c_double()
         check(lib.spde_logdet(self.plan.h, which, ctypes.byref(out), _stream()))

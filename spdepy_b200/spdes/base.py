@@ -406,9 +406,11 @@ class SPDE2D:
         st = self._assemble(par)
         self._state = st
         Q = st["Q"]
-        eng.factorize(0, Q)
+        eng.factorize_async(0, Q)               # the two factorisations run concurrently
+        eng.factorize_async(1, Q, cnt, tau)
+        eng.factor_wait(0)
+        eng.factor_wait(1)
         ldQ = eng.logdet(0)
-        eng.factorize(1, Q, cnt, tau)
         ldQc = eng.logdet(1)
         mu_c = eng.solve(1, eng.scatter_obs(data, obs, tau))          # Q_c^-1 S^T data tau
         quad = Engine.dot(mu_c, eng.q_apply(Q, mu_c))
@@ -418,8 +420,7 @@ class SPDE2D:
         if not grad:
             return -like / (nobs * r)
         if exact_grad:
-            Z = eng.selinv(0)
-            Zc = eng.selinv(1)
+            Z, Zc = eng.selinv_pair()
             nd = eng.nslots // 2
             tr_tau = Engine.dot(cnt, Zc[nd * eng.n:(nd + 1) * eng.n].contiguous()) * tau
             W = (Z - Zc) * (0.5 * r)
