@@ -243,8 +243,14 @@ struct LevelBuilder {
         L.variant = variant;
         L.task0 = (int64_t)prog.gemm.size();
         L.tile0 = (int64_t)prog.tiles.size();
+        // longest tiles first: CTAs are dispatched in tile order, so the long-K tiles of the big fronts start
+        // early and the short ones fill the tail (LPT packing of one grouped launch)
+        std::vector<int> order;
         for (const Step *st : steps)
-            for (int g = st->g0; g < st->g0 + st->gn; g++) {
+            for (int g = st->g0; g < st->g0 + st->gn; g++) order.push_back(g);
+        std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return pool[x].K > pool[y].K; });
+        for (int g : order) {
+            {
                 const GemmTask &t = pool[g];
                 const int id = (int)(prog.gemm.size() - L.task0);
                 prog.gemm.push_back(t);
@@ -257,6 +263,7 @@ struct LevelBuilder {
                     }
                 prog.flops += 2.0 * t.M * t.N * t.K * (lower ? 0.5 : 1.0);
             }
+        }
         L.ntasks = (int)(prog.gemm.size() - L.task0);
         L.ntiles = (int)(prog.tiles.size() - L.tile0);
         if (L.ntiles > 0) prog.launches.push_back(L);

@@ -276,7 +276,79 @@ class SPDE2D:
         self._state = st
         fac = self.engine.factorize(0, st["Q"])
         Q = self.engine.to_scipy(st["Q"])
-        return Q, fac, ([] if grad else None)
+        return Q, fac, (self._lazy_dQ(st) if grad else None)
+
+    # ------------------------------------------------------------------ dQ/dtheta_i as lazy operators
+    def _Q_from(self, st, A9, kappa):
+        """Precision (slot layout) for a given operator stencil and kappa field, without the initial-field block."""
+        eng = self.engine
+        if not self.timed:
+            return eng.atda(A9, kappa, st["V"], 0)
+        AtDA = eng.atda(A9, kappa, st["V"], 1)
+        zero0 = torch.zeros(25 * eng.Ns, dtype=F64, device=A9.device)
+        return eng.fill_spacetime(AtDA, A9, kappa, st["V"], zero0, st["sigma"], st["dt"], self.divide)
+
+    def _direction_stencils(self, st):
+        """(kind, payload) per own parameter, in the reference's dQ order."""
+        g, eng = self.grid, self.engine
+        V, dt = st["V"], st["dt"]
+        out = []
+        nk = self.Np if self.kvar else 1
+        for i in range(nk):
+            out.append(("kappa", i))
+        _, dirs = self._H_and_dirs(st["p"], want_dirs=True)
+        for dH in dirs:
+            ah = eng.ah_stencil(g.hx, g.hy, to_dev(dH), self.Hvar)
+            out.append(("dA", eng.combine_A(3 if self.timed else 5, V, dt, st["kappa"], ah, None)))
+        if self.wkind is not None:
+            wsd = to_dev(st["ws"])
+            if self.wkind == "const":
+                for d in (1, 2):
+                    aw = eng.aw_stencil(g.hx, g.hy, wsd, None, False, d, False)
+                    out.append(("dA", eng.combine_A(4, V, dt, st["kappa"], None, aw)))
+            else:
+                for i in range(2 * self.Np):
+                    dpar = np.zeros(2 * self.Np)
+                    dpar[i] = 1
+                    dws = to_dev(np.ascontiguousarray(g.evalAdv(dpar)))
+                    aw = eng.aw_stencil(g.hx, g.hy, wsd, dws, True, 1 if i < self.Np else 2, True)
+                    out.append(("dA", eng.combine_A(4, V, dt, st["kappa"], None, aw)))
+        if self.timed:
+            out.append(("sigma", None))
+        return out
+
+    def _dQ_slots(self, st, kind, payload):
+        """Slot array of one dQ/dtheta_i.  Q is exactly quadratic in the operator stencil A and linear in
+        Qs = kappa^2 V, so symmetric / forward differences of the *assembly kernels* with O(1) steps
+        reproduce the reference's analytic dQ (advection_diffusion2D.py:119-182) to rounding."""
+        eng = self.engine
+        A9, kap = st["A9"], st["kappa"]
+        Ns = eng.Ns
+        if kind == "sigma":
+            Qnp = self._Q_from(st, A9, kap)
+            return -Qnp
+        if kind == "dA":
+            dA = payload
+            s = float(A9.abs().max() / dA.abs().max().clamp_min(1e-300))       # comparable magnitudes: well conditioned
+            return (self._Q_from(st, A9 + s * dA, kap) - self._Q_from(st, A9 - s * dA, kap)) / (2 * s)
+        # log kappa (spline coefficient i or the scalar): dA on the centre slot + the linear Qs dependence
+        bs = self._bs_dev()[:, payload] if self.kvar else torch.ones(1, dtype=F64, device=A9.device)
+        dA = torch.zeros_like(A9)
+        dA[4 * Ns:5 * Ns] = st["V"] * kap * bs * (st["dt"] if self.timed else 1.0)
+        s = float(A9.abs().max() / dA.abs().max().clamp_min(1e-300))
+        out = (self._Q_from(st, A9 + s * dA, kap) - self._Q_from(st, A9 - s * dA, kap)) / (2 * s)
+        if self.timed:
+            h = 0.25
+            kap2 = kap * torch.sqrt(1 + 2 * h * bs)          # Qs -> Qs (1 + 2 h bs) = Qs + h dQs
+            out = out + (self._Q_from(st, A9, kap2) - self._Q_from(st, A9, kap)) / h
+        return out
+
+    def _lazy_dQ(self, st):
+        ops = [LazyDQ(self, st, kind, payload) for kind, payload in self._direction_stencils(st)]
+        if self.timed and st["joint"]:
+            for op0 in self.mod0._lazy_dQ(st["mod0"]):
+                ops.append(LazyDQ(self, st, "q0", op0))
+        return ops
 
     # public stencil wrappers with the reference's return type (advection_diffusion2D.py:226-260)
     def _stencil_to_csc(self, a9):
@@ -442,3 +514,39 @@ class SPDE2D:
         g_par[:len(gi)] = gi
         g_par[-1] = nobs * r / 2 - 1 / 2 * tr_tau * r - tau / 2 * resid
         return -like / (nobs * r), -g_par / (nobs * r)
+
+
+class LazyDQ:
+    """One ``dQ/dtheta_i`` of the reference's ``dQ`` list (``advection_diffusion2D.py:119-182``) as an operator:
+    ``dQ[i] @ X`` (NumPy or CUDA tensor, (n,) or (n,k)) and ``dQ[i].tocsc()``.  Built on demand on the device."""
+
+    def __init__(self, model, st, kind, payload):
+        self.model, self.st, self.kind, self.payload = model, st, kind, payload
+        self._slots = None
+        n = model.engine.n
+        self.shape = (n, n)
+
+    def slots(self):
+        if self._slots is None:
+            m, eng = self.model, self.model.engine
+            if self.kind == "q0":       # initial-field parameter: blockdiag(dQ0_j, 0, ..., 0)
+                s = torch.zeros(eng.nslots * eng.n, dtype=F64, device=self.st["A9"].device)
+                s0 = self.payload.slots().view(25, eng.Ns)
+                s.view(eng.nslots, eng.n)[9:34, :eng.Ns] = s0
+                self._slots = s
+            else:
+                self._slots = m._dQ_slots(self.st, self.kind, self.payload)
+        return self._slots
+
+    def __matmul__(self, X):
+        eng = self.model.engine
+        is_np = not isinstance(X, torch.Tensor)
+        x = to_dev(np.asarray(X, dtype=np.float64) if is_np else X)
+        one = x.dim() == 1
+        y = eng.q_apply(self.slots(), x.reshape(eng.n, -1).contiguous())
+        if one:
+            y = y.reshape(-1)
+        return to_host(y) if is_np else y
+
+    def tocsc(self):
+        return self.model.engine.to_scipy(self.slots())

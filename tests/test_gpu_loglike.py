@@ -127,3 +127,20 @@ def test_not_positive_definite_raises():
     Q[(eng.nslots // 2) * eng.n + 3] = -1.0
     with pytest.raises(NotPositiveDefiniteError):
         eng.factorize(0, Q)
+
+
+@pytest.mark.parametrize("name", ["wm_ani_bc1_ext", "varwm_ani_bc2", "ad_ani_bc3_q0", "ad_ha_bc1_q0", "vavd_ani_bc1_ext_q0"])
+def test_lazy_dQ_operators_vs_oracle(name):
+    """makeQ(grad=True) returns dQ as lazy operators; dQ[i] @ X must equal the reference's explicit matrices."""
+    d = load_golden(name)
+    mod = _build(d)
+    Q, fac, dQ = mod.mod.makeQ(d["par"], grad=True)
+    orc = make_oracle(d)
+    Qo, _, dQo = orc.makeQ(d["par"], grad=True)
+    assert len(dQ) == len(dQo) == d["par"].size - 1
+    X = np.random.default_rng(0).normal(size=(Q.shape[0], 3))
+    for i in range(len(dQ)):
+        ref = dQo[i] @ X
+        got = dQ[i] @ X
+        assert np.abs(got - ref).max() <= 1e-9 * max(np.abs(ref).max(), 1e-300), (i, np.abs(got - ref).max(), np.abs(ref).max())
+    assert abs(dQ[0].tocsc() - dQo[0]).max() <= 1e-9 * abs(dQo[0]).max()
