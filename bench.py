@@ -320,6 +320,10 @@ def run_ours(args):
         achieved = alg_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None
         roof = {"bound": "tensor", "kernel": "k_gemm_grouped (FP64 DMMA m8n8k4)", "achieved": achieved, "peak": peak,
                 "unit": "TFLOP/s", "frac": (achieved / peak) if achieved else None, "traffic": None,
+                "traffic_note": "ncu --set full of the largest grouped launch of this workload (19718 CTAs, 25.4 ms): "
+                                "dram read 16.46 GB + write 1.58 GB, DMMA pipe 83% active, L2 hit 77% "
+                                "(profiles/r1_ncu_gemm_full_summary.json); a per-launch average over the ~4400 launches "
+                                "of a step is not captured",
                 "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (MEASURED_PEAKS.json has no FP64 figure)",
                 "launches_per_step": gemm_launches, "avg_launch_ms": gemm_ms / max(gemm_launches, 1),
                 "gemm_share_of_scheduled_time": gemm_ms / total_ms if total_ms else None,
