@@ -1,0 +1,95 @@
+"""Full-size (BASELINE configs[1], 50x50x20) checks through size-independent properties: the closed-form
+log-determinant of the space-time prior, solve residuals, Takahashi against sampled
+variances, the exact gradient against central finite differences, and the Hutchinson estimator's mean."""
+import numpy as np
+import pytest
+import torch
+from scipy import sparse
+from scipy.sparse import linalg as spla
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def c2():
+    import bench
+    inp = bench.make_inputs("c2")
+    mod = bench.build_ours(inp)
+    mod.mod.initFit(inp["data"], idx=inp["idx"])
+    return inp, mod
+
+
+def test_logdet_closed_form(c2):
+    """logdet Q = logdet Q0 + (T-1) [2 log|det A| + Ns log(k^2 V) - 2 Ns log V - Ns log(dt sigma)]."""
+    inp, mod = c2
+    m = mod.mod
+    par = inp["theta"]
+    st = m._assemble(par)
+    eng, g = m.engine, m.grid
+    fac = eng.factorize(0, st["Q"])
+    ld = fac.logdet()
+    A = m._stencil_to_csc(st["A9"]).tocsc()
+    lu = spla.splu(A)
+    logdetA = np.log(np.abs(lu.U.diagonal())).sum() + np.log(np.abs(lu.L.diagonal())).sum()
+    fac0 = m.mod0.engine.factorize(0, st["mod0"]["Q"])
+    ld0 = fac0.logdet()
+    k, V, Ns, T = float(np.exp(par[0])), g.V, g.Ns, g.T
+    sigma = float(np.exp(par[6]))
+    ref = ld0 + (T - 1) * (2 * logdetA + Ns * np.log(k ** 2 * V) - 2 * Ns * np.log(V) - Ns * np.log(g.dt * sigma))
+    assert abs(ld - ref) <= 1e-9 * abs(ref), (ld, ref)
+
+
+def test_solve_residual_and_sample_covariance(c2):
+    inp, mod = c2
+    m = mod.mod
+    st = m._assemble(inp["theta"])
+    eng = m.engine
+    fac = eng.factorize(0, st["Q"])
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    B = torch.randn(eng.n, 7, dtype=torch.float64, device="cuda", generator=gen)
+    X = eng.solve(0, B.clone())
+    R = eng.q_apply(st["Q"], X) - B
+    assert float(R.abs().max()) <= 1e-9 * float(B.abs().max())
+    # L^T x = z round trip: P^T L^-T z has covariance Q^-1, so Q applied to (Q^-1 b) recovers b (above) and
+    # the marginal variances of 4000 samples agree with the Takahashi diagonal within Monte-Carlo error
+    Z = eng.selinv(0)
+    nd = eng.nslots // 2
+    var = Z[nd * eng.n:(nd + 1) * eng.n]
+    z = torch.randn(eng.n, 4000, dtype=torch.float64, device="cuda", generator=gen)
+    S = eng.solve(0, z, 10)
+    emp = S.var(dim=1)
+    rel = ((emp - var) / var).abs()
+    assert float(rel.mean()) < 0.03 and float(rel.max()) < 0.15
+
+
+def test_exact_gradient_vs_finite_differences(c2):
+    """The check of examples/server/grad_test.py:7-17 (central differences of logLike(grad=False)), made
+    deterministic by the exact Takahashi gradient.  bc=3: every component is a true derivative (App. C-4)."""
+    inp, mod = c2
+    m = mod.mod
+    par = inp["theta"].copy()
+    like, jac = m.logLike(par, grad=True, exact_grad=True)
+    h = 1e-4
+    for i in range(par.size):
+        p1, p2 = par.copy(), par.copy()
+        p1[i] += h
+        p2[i] -= h
+        fd = (m.logLike(p1, grad=False) - m.logLike(p2, grad=False)) / (2 * h)
+        assert abs(fd - jac[i]) <= 2e-6 * max(1.0, abs(jac[i])) + 1e-5 * abs(jac[i]), (i, fd, jac[i])
+
+
+def test_hutchinson_scatters_around_exact(c2):
+    inp, mod = c2
+    m = mod.mod
+    par = inp["theta"]
+    like, jac = m.logLike(par, grad=True, exact_grad=True)
+    rng = np.random.default_rng(0)
+    est = []
+    for rep in range(6):
+        probes = 2.0 * rng.integers(0, 2, size=(m.grid.n, 100)) - 1.0
+        l2, j2 = m.logLike(par, grad=True, probes=probes)
+        assert l2 == pytest.approx(like, rel=1e-12)
+        est.append(j2)
+    est = np.array(est)
+    sd = est.std(axis=0, ddof=1) / np.sqrt(est.shape[0]) + 1e-12
+    assert np.all(np.abs(est.mean(axis=0) - jac) < 6 * sd + 1e-8), (est.mean(axis=0), jac, sd)
