@@ -40,6 +40,9 @@ CASES = [
     ("vavd_ani_bc1_ext_q0", "var-advection-var-diffusion", False, True, 1, (8, 7, 3), 2, "var-whittle-matern", True),
     ("vavd_ani_bc3", "var-advection-var-diffusion", False, True, 3, (8, 7, 3), None, "var-whittle-matern", False),
     ("vavd_ani_bc2", "var-advection-var-diffusion", False, True, 2, (8, 7, 3), None, "var-whittle-matern", False),
+    ("avhd_bc3", "advection-var-diffusion", True, True, 3, (8, 7, 3), None, "whittle-matern", False),
+    ("vahd_bc1_ext_q0", "var-advection-diffusion", True, True, 1, (8, 7, 3), 2, "whittle-matern", True),
+    ("vavhd_bc3", "var-advection-var-diffusion", True, True, 3, (8, 7, 3), None, "whittle-matern", False),
     ("vavd_iso_bc3_q0", "var-advection-var-diffusion", False, False, 3, (8, 7, 3), None, "whittle-matern", True),
 ]
 

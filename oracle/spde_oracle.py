@@ -60,6 +60,9 @@ SPECS = {
     "advection-var-idiffusion-2D": Spec("advection-var-idiffusion-2D", True, True, "iso", True, "const", "paren"),
     "var-advection-diffusion-2D": Spec("var-advection-diffusion-2D", True, False, "aniso", False, "var", "paren"),
     "var-advection-idiffusion-2D": Spec("var-advection-idiffusion-2D", True, False, "iso", False, "var", "paren"),
+    "advection-var-ha-diffusion-2D": Spec("advection-var-ha-diffusion-2D", True, True, "ha", True, "const", "sum"),
+    "var-advection-ha-diffusion-2D": Spec("var-advection-ha-diffusion-2D", True, False, "ha", False, "var", "paren"),
+    "var-advection-var-ha-diffusion-2D": Spec("var-advection-var-ha-diffusion-2D", True, True, "ha", True, "var", "paren", "div"),
     "var-advection-var-diffusion-2D": Spec("var-advection-var-diffusion-2D", True, True, "aniso", True, "var", "paren", "div"),
     "var-advection-var-idiffusion-2D": Spec("var-advection-var-idiffusion-2D", True, True, "iso", True, "var", "paren", "div"),
 }
@@ -221,6 +224,28 @@ class OracleSPDE:
             return Hs, dirs
         gamma = np.exp(g.evalBH(par=p["gamma"]))
         eye = np.eye(2)
+        if sp.H == "ha":        # advection_var_ha_diffusion2D.py:104-113,145-175
+            vx, vy = g.evalBH(p["vx"]), g.evalBH(p["vy"])
+            aV = np.sqrt(vx ** 2 + vy ** 2)
+            mV = np.array([[vx, vy], [vy, -vx]]).T.swapaxes(0, 1)
+            ch = (np.exp(aV) + np.exp(-aV)) / 2
+            sh = (np.exp(aV) - np.exp(-aV)) / 2
+            nx = np.newaxis
+            Hs = (gamma * ch)[:, :, nx, nx] * eye + (gamma * sh / aV)[:, :, nx, nx] * mV
+            for i in range(self.Np):
+                dg = g.bsH[:, :, i] * gamma
+                dirs.append(("gamma", (dg * ch)[:, :, nx, nx] * eye + (dg * sh / aV)[:, :, nx, nx] * mV))
+            for comp in (0, 1):
+                for i in range(self.Np):
+                    dpar = np.zeros(self.Np)
+                    dpar[i] = 1
+                    dv = g.evalBH(par=dpar)
+                    z = vx * 0
+                    dmV = (np.array([[dv, z], [z, -dv]]) if comp == 0 else np.array([[z, dv], [dv, -z]])).T.swapaxes(0, 1)
+                    vc = vx if comp == 0 else vy
+                    dirs.append(("v", (gamma * dv * vc / aV)[:, :, nx, nx] * (sh[:, :, nx, nx] * eye + ((ch - sh / aV) / aV)[:, :, nx, nx] * mV)
+                                 + (gamma * sh / aV)[:, :, nx, nx] * dmV))
+            return Hs, dirs
         if sp.H == "iso":
             Hs = eye * (np.stack([gamma, gamma], axis=2))[:, :, :, np.newaxis]
         else:
@@ -239,8 +264,6 @@ class OracleSPDE:
                     b = g.evalBH(par=dpar)
                     dv = np.stack([b, zero], axis=2) if comp == 0 else np.stack([zero, b], axis=2)
                     dirs.append(("v", vv[:, :, :, np.newaxis] * dv[:, :, np.newaxis, :] + dv[:, :, :, np.newaxis] * vv[:, :, np.newaxis, :]))
-        elif sp.H == "ha":
-            raise NotImplementedError("spatially varying half-angle diffusion is not restated yet")
         return Hs, dirs
 
     # --- spatial model

@@ -36,6 +36,14 @@ VarAdvectionDiffusion2D = _cls("VarAdvectionDiffusion2D", "var-advection-diffusi
                                wkind="var", aflav=2, default_own=(-1, -1, 0.1, 0.1, [0.1] * 18, 0))
 VarAdvectionIDiffusion2D = _cls("VarAdvectionIDiffusion2D", "var-advection-idiffusion-2D", timed=True, Hkind="iso",
                                 wkind="var", aflav=2, default_own=(-1, -1, [0.01] * 18, 0))
+AdvectionVarHaDiffusion2D = _cls("AdvectionVarHaDiffusion2D", "advection-var-ha-diffusion-2D", timed=True, kvar=True, Hkind="ha",
+                                 Hvar=True, wkind="const", aflav=1,
+                                 default_own=([-1] * N9, [-1] * N9, [0.1] * N9, [0.1] * N9, 0.1, 0.1, 0))
+VarAdvectionHaDiffusion2D = _cls("VarAdvectionHaDiffusion2D", "var-advection-ha-diffusion-2D", timed=True, Hkind="ha",
+                                 wkind="var", aflav=2, default_own=(-1, -1, 0.1, 0.1, [0.1] * 18, 0))
+VarAdvectionVarHaDiffusion2D = _cls("VarAdvectionVarHaDiffusion2D", "var-advection-var-ha-diffusion-2D", timed=True,
+                                    kvar=True, Hkind="ha", Hvar=True, wkind="var", aflav=2, divide=True,
+                                    default_own=([-1] * N9, [-1] * N9, [0.1] * 18, [0.1] * 18, 0))
 VarAdvectionVarDiffusion2D = _cls("VarAdvectionVarDiffusion2D", "var-advection-var-diffusion-2D", timed=True, kvar=True,
                                   Hkind="aniso", Hvar=True, wkind="var", aflav=2, divide=True,
                                   default_own=([-1] * N9, [-1] * N9, [0.1] * 18, [0.1] * 18, 0))
@@ -48,9 +56,9 @@ _TABLE = {
     ("whittle-matern", 1): (WhittleMaternHa2D, WhittleMaternAnisotropic2D, WhittleMatern2D),
     ("var-whittle-matern", -1): (None, VarWhittleMaternAnisotropic2D, None),
     ("advection-diffusion", 2): (AdvectionHaDiffusion2D, AdvectionDiffusion2D, AdvectionIDiffusion2D),
-    ("advection-var-diffusion", 3): (None, AdvectionVarDiffusion2D, AdvectionVarIDiffusion2D),
-    ("var-advection-diffusion", 6): (None, VarAdvectionDiffusion2D, VarAdvectionIDiffusion2D),
-    ("var-advection-var-diffusion", 7): (None, VarAdvectionVarDiffusion2D, VarAdvectionVarIDiffusion2D),
+    ("advection-var-diffusion", 3): (AdvectionVarHaDiffusion2D, AdvectionVarDiffusion2D, AdvectionVarIDiffusion2D),
+    ("var-advection-diffusion", 6): (VarAdvectionHaDiffusion2D, VarAdvectionDiffusion2D, VarAdvectionIDiffusion2D),
+    ("var-advection-var-diffusion", 7): (VarAdvectionVarHaDiffusion2D, VarAdvectionVarDiffusion2D, VarAdvectionVarIDiffusion2D),
 }
 _NEXT = {"cov-advection-diffusion": 4, "cov-advection-var-diffusion": 5, "seperable-spatial-temporal": 8}
 

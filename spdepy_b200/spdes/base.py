@@ -210,8 +210,25 @@ class SPDE2D:
             vv = np.stack([g.evalBH(p["vx"]), g.evalBH(p["vy"])], axis=2)
             H = H + vv[:, :, :, None] * vv[:, :, None, :]
             self._face_fields.update(vx=vv[:, :, 0], vy=vv[:, :, 1])
-        elif self.Hkind == "ha":
-            raise NotImplementedError("spatially varying half-angle diffusion: next round (SURVEY.md section 8f)")
+        elif self.Hkind == "ha":        # advection_var_ha_diffusion2D.py:104-113
+            vx, vy = g.evalBH(p["vx"]), g.evalBH(p["vy"])
+            aV = np.sqrt(vx ** 2 + vy ** 2)
+            mV = np.array([[vx, vy], [vy, -vx]]).T.swapaxes(0, 1)
+            ch, sh = (np.exp(aV) + np.exp(-aV)) / 2, (np.exp(aV) - np.exp(-aV)) / 2
+            H = (gam * ch)[:, :, None, None] * I2 + (gam * sh / aV)[:, :, None, None] * mV
+            self._face_fields.update(vx=vx, vy=vy)
+            if want_dirs:
+                for i in range(self.Np):
+                    dg = g.bsH[:, :, i] * gam
+                    dirs.append((dg * ch)[:, :, None, None] * I2 + (dg * sh / aV)[:, :, None, None] * mV)
+                for comp in (0, 1):
+                    for i in range(self.Np):
+                        dv, z = g.bsH[:, :, i], vx * 0
+                        dmV = (np.array([[dv, z], [z, -dv]]) if comp == 0 else np.array([[z, dv], [dv, -z]])).T.swapaxes(0, 1)
+                        vc = vx if comp == 0 else vy
+                        dirs.append((gam * dv * vc / aV)[:, :, None, None] * (sh[:, :, None, None] * I2 + ((ch - sh / aV) / aV)[:, :, None, None] * mV)
+                                    + (gam * sh / aV)[:, :, None, None] * dmV)
+            return H, dirs
         if want_dirs:
             for i in range(self.Np):
                 dg = g.bsH[:, :, i] * gam
@@ -412,7 +429,22 @@ class SPDE2D:
             D = torch.stack([GH[0], GH[1], GH[6], GH[7]], dim=1)        # dS/d(H00 at W,E), d(H11 at S,N)
             bsH = self._bsH_dev()
             out.extend(to_host(sgn * eng.gemv_t(bsH, (f["gam"] * D).reshape(-1).contiguous())).tolist())
-            if self.Hkind == "aniso":
+            if self.Hkind == "ha":
+                # half-angle parametrisation H = gamma (cosh|v| I + sinh|v|/|v| [[vx,vy],[vy,-vx]])
+                out = out[:-self.Np]                                    # gamma block recomputed below (dH/dlog gamma = H)
+                O = torch.stack([GH[2], GH[3], GH[4], GH[5]], dim=1)
+                vx, vy, gam = f["vx"], f["vy"], f["gam"]
+                a = torch.sqrt(vx * vx + vy * vy)
+                ch, sh = torch.cosh(a), torch.sinh(a)
+                s = sh / a
+                ds = (ch - s) / a
+                sg = torch.tensor([1.0, 1.0, -1.0, -1.0], dtype=F64, device=a.device)   # H00 on W,E ; H11 on S,N
+                u_g = gam * ((ch + sg * s * vx) * D + s * vy * O)
+                u_vx = gam * ((sh * vx / a + sg * (ds * vx / a * vx + s)) * D + ds * vx / a * vy * O)
+                u_vy = gam * ((sh * vy / a + sg * (ds * vy / a * vx)) * D + (ds * vy / a * vy + s) * O)
+                for u in (u_g, u_vx, u_vy):
+                    out.extend(to_host(sgn * eng.gemv_t(bsH, u.reshape(-1).contiguous())).tolist())
+            elif self.Hkind == "aniso":
                 O = torch.stack([GH[2], GH[3], GH[4], GH[5]], dim=1)    # dS/d(H10 at W,E), d(H01 at S,N)
                 vx, vy = f["vx"], f["vy"]
                 u_vx = torch.cat([2 * vx[:, :2] * D[:, :2] + vy[:, :2] * O[:, :2], vy[:, 2:] * O[:, 2:]], dim=1)
