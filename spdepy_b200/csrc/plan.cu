@@ -63,68 +63,81 @@ __global__ void k_extend_add(const ExtTask *__restrict__ tasks, const TileRef *_
 }
 
 // ---------------------------------------------------------------------------------------------
-// POTRF of one diagonal block (b <= 64) together with the explicit inverse W = L^-1 of the factor.
-// One CTA per block, register resident: thread (r, q) = (tid % 64, tid / 64) keeps columns 16q..16q+15 of
-// row r of the block AND of W in registers (the column loop is fully unrolled, so all register indices
-// are static).  Step j broadcasts the unscaled pivot column of A and row j of W through a double-buffered
-// 2 x 64 shared-memory line; every thread recomputes 1/l_jj = rsqrt(a_jj) itself, so each step costs one
-// barrier, ~34 shared loads and 32 FMAs.  The inverse comes out of the same sweep: W <- E_j W with the
-// elementary operation of step j (scale row j, eliminate it from the rows below).
+// POTRF of one diagonal block (b <= 64) in shared memory + explicit inverse of the factor.
+// One CTA per block; right-looking column sweep, then forward substitution on the identity.
 __global__ void __launch_bounds__(256) k_potrf(const PotrfTask *__restrict__ tasks, double *__restrict__ L,
                                                double *__restrict__ dinv, int *__restrict__ status)
 {
-    __shared__ double colbuf[2][NB];
-    __shared__ double rowbuf[2][NB];
+    // lower triangle: the block / its factor; strict upper triangle: W^T (W = L^-1); wd: diag(W)
+    __shared__ double a[NB][NB + 1];
+    __shared__ double wd[NB];
     __shared__ int bad;
     const PotrfTask t = tasks[blockIdx.x];
     double *blk = L + t.blk;
     const int b = t.b, tid = threadIdx.x;
-    const int r = tid & 63, q = tid >> 6, c0 = q * 16;
     if (tid == 0) bad = -1;
-    double a[16], w[16];
-#pragma unroll
-    for (int cc = 0; cc < 16; cc++) {
-        const int c = c0 + cc;
-        // rows / columns beyond b behave as an identity block
-        a[cc] = (r < b && c < b) ? ((r >= c) ? blk[r + (long long)c * t.ld] : 0.0) : (r == c ? 1.0 : 0.0);
-        w[cc] = (r == c) ? 1.0 : 0.0;
+    for (int e = tid; e < NB * NB; e += 256) {
+        const int i = e % NB, j = e / NB;
+        a[i][j] = (i < b && j < b && i >= j) ? blk[i + (long long)j * t.ld] : 0.0;
     }
+    if (tid < NB) wd[tid] = 0.0;
     __syncthreads();
-#pragma unroll
-    for (int j = 0; j < NB; j++) {
-        const int qj = j >> 4, cj = j & 15, s = j & 1;
-        if (q == qj) colbuf[s][r] = a[cj];                 // column j of the (updated) block, unscaled
-        if (r == j) {
-#pragma unroll
-            for (int cc = 0; cc < 16; cc++) rowbuf[s][c0 + cc] = w[cc];   // row j of W, unscaled
+    // Right-looking sweep, one barrier per column: every thread owns row i = tid % 64 and a quarter of
+    // the columns; the pivot sqrt / reciprocal are recomputed by all threads instead of broadcast.
+    {
+        const int i = tid & 63, ty = tid >> 6;
+        for (int j = 0; j < b; j++) {
+            const double d = a[j][j];
+            const bool ok = d > 0.0;
+            const double inv = ok ? rsqrt(d) : nan("");     // 1/l_jj; l_jj = d * inv
+            const bool mine = i > j && i < b;
+            const double li = mine ? a[i][j] * inv : 0.0;
+            if (mine) {
+                // a[i][c] -= l_ic * l_cj for my quarter of the columns, four independent updates in flight
+                int c = j + 1 + ty;
+                for (; c + 12 <= i; c += 16) {
+                    const double p0 = a[c][j], p1 = a[c + 4][j], p2 = a[c + 8][j], p3 = a[c + 12][j];
+                    const double t0 = a[i][c], t1 = a[i][c + 4], t2 = a[i][c + 8], t3 = a[i][c + 12];
+                    a[i][c] = t0 - li * (p0 * inv);
+                    a[i][c + 4] = t1 - li * (p1 * inv);
+                    a[i][c + 8] = t2 - li * (p2 * inv);
+                    a[i][c + 12] = t3 - li * (p3 * inv);
+                }
+                for (; c <= i; c += 4) a[i][c] -= li * (a[c][j] * inv);
+            }
+            __syncthreads();                       // column j has been read by everyone
+            if (ty == 0 && mine) a[i][j] = li;
+            if (tid == 0) { a[j][j] = d * inv; if (!ok && bad < 0) bad = j; }
         }
         __syncthreads();
-        const double d = colbuf[s][j];
-        const bool ok = d > 0.0;
-        const double inv = ok ? rsqrt(d) : nan("");
-        if (!ok && tid == 0 && bad < 0) bad = j;
-        const double lr = (r > j) ? colbuf[s][r] * inv : 0.0;   // L[r][j]
-        if (q == qj) a[cj] = (r > j) ? lr : ((r == j) ? d * inv : a[cj]);
-#pragma unroll
-        for (int cc = 0; cc < 16; cc++) {
-            const int c = c0 + cc;
-            // trailing update of A (columns j < c <= r) and elimination of row j from W (columns c <= j)
-            if (c > j) {
-                if (r >= c) a[cc] -= lr * (colbuf[s][c] * inv);
-            } else {
-                const double wj = (c == j) ? inv : rowbuf[s][c] * inv;
-                if (r > j) w[cc] -= lr * wj;
-                else if (r == j) w[cc] = wj;
-            }
+    }
+    // W = L^-1 by forward substitution on the identity.  Column c of W is kept in row c of the (free)
+    // upper triangle; four lanes share a column and split the dot product over k, so the dependent
+    // chain per row is ~(i-c)/4 FMAs plus two shuffles instead of i-c.
+    {
+        const int c = tid >> 2, l = tid & 3;
+        const bool live = c < b;
+        if (tid < NB) wd[tid] = tid < b ? 1.0 / a[tid][tid] : 0.0;
+        __syncthreads();
+        const double wcc = live ? wd[c] : 0.0;
+        for (int i = 1; i < NB; i++) {
+            double s = 0.0;
+            if (live && i > c && i < b)
+                for (int k = c + 1 + l; k < i; k += 4) s += a[i][k] * a[c][k];
+            s += __shfl_xor_sync(0xffffffffu, s, 1);
+            s += __shfl_xor_sync(0xffffffffu, s, 2);
+            if (live && l == 0 && i > c && i < b) a[c][i] = (-a[i][c] * wcc - s) * wd[i];
+            __syncwarp();
         }
     }
-#pragma unroll
-    for (int cc = 0; cc < 16; cc++) {
-        const int c = c0 + cc;
-        if (r < b && c < b) blk[r + (long long)c * t.ld] = (r >= c) ? a[cc] : 0.0;   // strict upper part written as 0
-        dinv[t.dinv + r + (long long)c * NB] = (r < b && c < b && r >= c) ? w[cc] : 0.0;
-    }
     __syncthreads();
+    for (int e = tid; e < NB * NB; e += 256) {
+        const int i = e % NB, j = e / NB;
+        if (i < b && j < b) blk[i + (long long)j * t.ld] = (i >= j) ? a[i][j] : 0.0;
+        double wv = 0.0;
+        if (i < b && j < b) wv = (i > j) ? a[j][i] : (i == j ? wd[i] : 0.0);
+        dinv[t.dinv + e] = wv;
+    }
     if (tid == 0 && bad >= 0) atomicCAS(status, 0, t.col0 + bad + 1);
 }
 
