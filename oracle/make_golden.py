@@ -43,6 +43,8 @@ CASES = [
     ("avhd_bc3", "advection-var-diffusion", True, True, 3, (8, 7, 3), None, "whittle-matern", False),
     ("vahd_bc1_ext_q0", "var-advection-diffusion", True, True, 1, (8, 7, 3), 2, "whittle-matern", True),
     ("vavhd_bc3", "var-advection-var-diffusion", True, True, 3, (8, 7, 3), None, "whittle-matern", False),
+    ("cad_ani_bc1_q0", "cov-advection-diffusion", False, True, 1, (8, 7, 3), None, "whittle-matern", True),
+    ("cavd_ha_bc3", "cov-advection-var-diffusion", True, True, 3, (8, 7, 3), None, "whittle-matern", False),
     ("vavd_iso_bc3_q0", "var-advection-var-diffusion", False, False, 3, (8, 7, 3), None, "whittle-matern", True),
 ]
 
@@ -82,6 +84,12 @@ def run_case(case):
         m0.mod.setQ(par=mod0_par)
         kw["mod0"] = m0
     mod = sp.model(grid=g, spde=spde, ha=ha, anisotropic=ani, bc=bc, **kw)
+    ww = np.zeros((0, 4))
+    if spde.startswith("cov-"):
+        # covariate-driven advection: the face velocities come from outside (cov_advection_diffusion2D.py:50-60)
+        ww = rng.normal(size=(g.Ns, 4))
+        mod.mod.ww = ww
+        mod.mod.dA_w = mod.mod.Aw(ww)
     par = theta_for(mod.mod, rng, fitQ0)
     rh.set_permutation(None)
     mod.mod.setQ(par=par)
@@ -92,7 +100,12 @@ def run_case(case):
     nobs = nprod // 3
     idx = np.sort(rng.choice(nprod, nobs, replace=False))
     data = X[idx, :2] + 0.1 * rng.normal(size=(nobs, 2))
-    mod.mod.initFit(data, idx=idx, fitQ0=fitQ0) if T is not None else mod.mod.initFit(data, idx=idx)
+    if spde.startswith("cov-"):
+        mod.mod.initFit(data, idx=idx, fitQ0=fitQ0, ww=ww)
+    elif T is not None:
+        mod.mod.initFit(data, idx=idx, fitQ0=fitQ0)
+    else:
+        mod.mod.initFit(data, idx=idx)
     nh1 = 16
     probes = rh.seeded_probes(g.n, nh1, 4)
     like, jac = rh.loglike_seeded(mod.mod, par, nh1=nh1, grad=True, seed=4)
@@ -115,7 +128,7 @@ def run_case(case):
         mod0_spde="" if mod0_spde is None else mod0_spde, fitQ0=fitQ0,
         x=x, y=y, t=np.zeros(0) if t is None else t, par=par,
         mod0_par=np.zeros(0) if mod0_par is None else mod0_par,
-        type=mod.mod.type,
+        type=mod.mod.type, ww=ww,
         Q_data=Q.data, Q_indices=Q.indices.astype(np.int32), Q_indptr=Q.indptr.astype(np.int32),
         sample=X, idx=idx, data=data, nh1=nh1, probes=probes.astype(np.int8),
         like=like, jac=jac, mu_c=mu_c, logdetQ=Qf.logdet(), logdetQc=Qcf.logdet(),

@@ -60,6 +60,12 @@ SPECS = {
     "advection-var-idiffusion-2D": Spec("advection-var-idiffusion-2D", True, True, "iso", True, "const", "paren"),
     "var-advection-diffusion-2D": Spec("var-advection-diffusion-2D", True, False, "aniso", False, "var", "paren"),
     "var-advection-idiffusion-2D": Spec("var-advection-idiffusion-2D", True, False, "iso", False, "var", "paren"),
+    "cov-advection-diffusion-2D": Spec("cov-advection-diffusion-2D", True, False, "aniso", False, "cov"),
+    "cov-advection-idiffusion-2D": Spec("cov-advection-idiffusion-2D", True, False, "iso", False, "cov"),
+    "cov-advection-ha-diffusion-2D": Spec("cov-advection-ha-diffusion-2D", True, False, "ha", False, "cov"),
+    "cov-advection-var-diffusion-2D": Spec("cov-advection-var-diffusion-2D", True, True, "aniso", True, "cov", "paren"),
+    "cov-advection-var-idiffusion-2D": Spec("cov-advection-var-idiffusion-2D", True, True, "iso", True, "cov", "paren"),
+    "cov-advection-var-ha-diffusion-2D": Spec("cov-advection-var-ha-diffusion-2D", True, True, "ha", True, "cov", "paren"),
     "advection-var-ha-diffusion-2D": Spec("advection-var-ha-diffusion-2D", True, True, "ha", True, "const", "sum"),
     "var-advection-ha-diffusion-2D": Spec("var-advection-ha-diffusion-2D", True, False, "ha", False, "var", "paren"),
     "var-advection-var-ha-diffusion-2D": Spec("var-advection-var-ha-diffusion-2D", True, True, "ha", True, "var", "paren", "div"),
@@ -72,7 +78,7 @@ def n_own_params(spec: Spec, Np: int = 9) -> int:
     """Number of the model's own parameters *excluding* log tau."""
     nk = Np if spec.kvar else 1
     nh = {"iso": 1, "aniso": 3, "ha": 3}[spec.H] * (Np if spec.Hvar else 1)
-    nw = 0 if spec.w is None else (2 if spec.w == "const" else 2 * Np)
+    nw = {None: 0, "const": 2, "cov": 1, "var": 2 * Np}[spec.w]
     return nk + nh + nw + (1 if spec.timed else 0)
 
 
@@ -134,7 +140,8 @@ class OracleSPDE:
     """Restatement of one reference model class; ``grid`` is any object with the reference grid
     attributes (``M N Ns n T hx hy V dt Dv iDv bs bsH bsA shape evalB evalBH evalAdv getS``)."""
 
-    def __init__(self, spec: Spec | str, grid, mod0: "OracleSPDE | None" = None, par=None, bc: int = 3):
+    def __init__(self, spec: Spec | str, grid, mod0: "OracleSPDE | None" = None, par=None, bc: int = 3, ww=None):
+        self.ww = ww      # cov-advection: supplied face velocities (cov_advection_diffusion2D.py:21)
         self.spec = SPECS[spec] if isinstance(spec, str) else spec
         self.grid = grid
         self.bc = bc
@@ -162,9 +169,11 @@ class OracleSPDE:
             tri = st.oracle_ah_face(M, N, Hs, self.grid.hx, self.grid.hy, self.bc)
         return st.to_csc(tri, M * N)
 
-    def Aw(self, ws, dws=None, diff=3):
+    def Aw(self, ws, dws=None, diff=3, nan_to_zero=True):
         M, N = self.grid.shape[0], self.grid.shape[1]
         ws = np.array(ws, dtype="float64")
+        if ws.ndim == 2 and not nan_to_zero:      # cov_advection_diffusion2D.py:225-240: no NaN filter
+            return st.to_csc(st.oracle_aw_face(M, N, ws, None, self.grid.hx, self.grid.hy, diff, self.bc), M * N)
         if ws.ndim == 1:
             return st.to_csc(st.oracle_aw_const(M, N, ws, self.grid.hx, self.grid.hy, diff, self.bc), M * N)
         tri = st.oracle_aw_face(M, N, ws, dws, self.grid.hx, self.grid.hy, diff, self.bc)
@@ -190,6 +199,9 @@ class OracleSPDE:
         elif sp.w == "var":
             out["w"] = par[o:o + 2 * Np]
             o += 2 * Np
+        elif sp.w == "cov":
+            out["w"] = par[o:o + 1]
+            o += 1
         if sp.timed:
             out["sigma"] = par[o]
             o += 1
@@ -316,14 +328,19 @@ class OracleSPDE:
             kappa = np.exp(p["kappa"][0])
             Dk = kappa * sparse.eye(Ns)
         Hs, dirs = self._H(p)
-        ws = p["w"] if sp.w == "const" else g.evalAdv(p["w"])
+        if sp.w == "cov":
+            ws = p["w"][0] * self.ww
+            Aw_val = self.Aw(ws, nan_to_zero=False)
+        else:
+            ws = p["w"] if sp.w == "const" else g.evalAdv(p["w"])
+            Aw_val = self.Aw(ws)
         sigma = np.exp(p["sigma"])
         As = Dv @ Dk
         Qs = As.transpose() @ iDv @ As
         if sp.aflav == "sum":
-            A = Dv + Dv @ Dk * dt - self.Ah(Hs) * dt + self.Aw(ws) * dt
+            A = Dv + Dv @ Dk * dt - self.Ah(Hs) * dt + Aw_val * dt
         else:
-            A = Dv + (Dv @ Dk - self.Ah(Hs) + self.Aw(ws)) * dt
+            A = Dv + (Dv @ Dk - self.Ah(Hs) + Aw_val) * dt
         n_own = p["n_own"]
         dQ0 = None
         if par.size > n_own + 1:
@@ -372,6 +389,8 @@ class OracleSPDE:
         if sp.w == "const":
             for d in (1, 2):
                 dQ.append(dQ_of_dA(self.Aw(ws, diff=d) * dt))
+        elif sp.w == "cov":
+            dQ.append(dQ_of_dA(self.Aw(self.ww, nan_to_zero=False) * dt))
         elif sp.w == "var":
             for i in range(2 * self.Np):
                 dpar = np.zeros(self.Np * 2)

@@ -51,16 +51,34 @@ VarAdvectionVarIDiffusion2D = _cls("VarAdvectionVarIDiffusion2D", "var-advection
                                    Hkind="iso", Hvar=True, wkind="var", aflav=2, divide=True,
                                    default_own=([-1] * N9, [-1] * N9, [0.1] * 18, 0))
 
+# covariate-driven advection: w = lambda * ww with supplied face velocities ww (cov_advection_*2D.py)
+CovAdvectionDiffusion2D = _cls("CovAdvectionDiffusion2D", "cov-advection-diffusion-2D", timed=True, Hkind="aniso", wkind="cov",
+                               aflav=1, default_own=(-1, -1, 0.1, 0.1, 0.1, 0))
+CovAdvectionIDiffusion2D = _cls("CovAdvectionIDiffusion2D", "cov-advection-idiffusion-2D", timed=True, Hkind="iso", wkind="cov",
+                                aflav=1, default_own=(-1, -1, 0.1, 0))
+CovAdvectionHaDiffusion2D = _cls("CovAdvectionHaDiffusion2D", "cov-advection-ha-diffusion-2D", timed=True, Hkind="ha",
+                                 wkind="cov", aflav=1, default_own=(-1, -1, 0.01, 0.01, 0.01, 0))
+CovAdvectionVarDiffusion2D = _cls("CovAdvectionVarDiffusion2D", "cov-advection-var-diffusion-2D", timed=True, kvar=True,
+                                  Hkind="aniso", Hvar=True, wkind="cov", aflav=2,
+                                  default_own=([-1] * N9, [-1] * N9, [0.1] * N9, [0.1] * N9, 0.1, 0))
+CovAdvectionVarIDiffusion2D = _cls("CovAdvectionVarIDiffusion2D", "cov-advection-var-idiffusion-2D", timed=True, kvar=True,
+                                   Hkind="iso", Hvar=True, wkind="cov", aflav=2, default_own=([-1] * N9, [-1] * N9, 0.1, 0))
+CovAdvectionVarHaDiffusion2D = _cls("CovAdvectionVarHaDiffusion2D", "cov-advection-var-ha-diffusion-2D", timed=True, kvar=True,
+                                    Hkind="ha", Hvar=True, wkind="cov", aflav=2,
+                                    default_own=([-1] * N9, [-1] * N9, [0.1] * N9, [0.1] * N9, 0.1, 0))
+
 _TABLE = {
     # model id -> (ha class, anisotropic class, isotropic class)
     ("whittle-matern", 1): (WhittleMaternHa2D, WhittleMaternAnisotropic2D, WhittleMatern2D),
     ("var-whittle-matern", -1): (None, VarWhittleMaternAnisotropic2D, None),
     ("advection-diffusion", 2): (AdvectionHaDiffusion2D, AdvectionDiffusion2D, AdvectionIDiffusion2D),
     ("advection-var-diffusion", 3): (AdvectionVarHaDiffusion2D, AdvectionVarDiffusion2D, AdvectionVarIDiffusion2D),
+    ("cov-advection-diffusion", 4): (CovAdvectionHaDiffusion2D, CovAdvectionDiffusion2D, CovAdvectionIDiffusion2D),
+    ("cov-advection-var-diffusion", 5): (CovAdvectionVarHaDiffusion2D, CovAdvectionVarDiffusion2D, CovAdvectionVarIDiffusion2D),
     ("var-advection-diffusion", 6): (VarAdvectionHaDiffusion2D, VarAdvectionDiffusion2D, VarAdvectionIDiffusion2D),
     ("var-advection-var-diffusion", 7): (VarAdvectionVarHaDiffusion2D, VarAdvectionVarDiffusion2D, VarAdvectionVarIDiffusion2D),
 }
-_NEXT = {"cov-advection-diffusion": 4, "cov-advection-var-diffusion": 5, "seperable-spatial-temporal": 8}
+_NEXT = {"seperable-spatial-temporal": 8}
 
 
 def spde_init(model, grid, parameters=None, ani=True, ha=True, bc=3, mod0=None):

@@ -36,8 +36,9 @@ class SPDE2D:
     divide = False       # Q / (dt*sigma) instead of (1/(dt*sigma)) * Q
     default_own = ()     # default own parameters (without mod0 block and tau)
 
-    def __init__(self, grid, mod0=None, par=None, bc=3) -> None:
+    def __init__(self, grid, mod0=None, par=None, bc=3, ww=None) -> None:
         self.grid = grid
+        self.ww = None if ww is None else np.ascontiguousarray(ww, dtype="float64")   # cov-advection: face velocities
         self.type = "%s-bc%d" % (self.name, bc)
         self.Q = None
         self.Q_fac = None
@@ -57,8 +58,9 @@ class SPDE2D:
         if bc == 2 and not self.Hvar:
             raise ValueError("bc=2 with a constant diffusion tensor is undefined in the reference "
                              "(AcH_2D_b2.cpp:105 returns NaN); use a var-* model")
-        if par is None:
-            self.setPars(self._default_par(joint=False))
+        if par is None or (self.wkind == "cov" and self.ww is None):
+            # (the cov-advection classes of the reference never assemble in __init__, cov_advection_diffusion2D.py:26-28)
+            self.setPars(self._default_par(joint=False) if par is None else par)
         else:
             self.setQ(par=par)
 
@@ -79,7 +81,7 @@ class SPDE2D:
     def n_own(self) -> int:
         nk = self.Np if self.kvar else 1
         nh = {"iso": 1, "aniso": 3, "ha": 3}[self.Hkind] * (self.Np if self.Hvar else 1)
-        nw = 0 if self.wkind is None else (2 if self.wkind == "const" else 2 * self.Np)
+        nw = {None: 0, "const": 2, "cov": 1, "var": 2 * self.Np}[self.wkind]
         return nk + nh + nw + (1 if self.timed else 0)
 
     def _split(self, par):
@@ -99,6 +101,9 @@ class SPDE2D:
         elif self.wkind == "var":
             p["w"] = par[o:o + 2 * self.Np]
             o += 2 * self.Np
+        elif self.wkind == "cov":
+            p["w"] = par[o:o + 1]
+            o += 1
         if self.timed:
             p["sigma"] = par[o]
             o += 1
@@ -121,6 +126,8 @@ class SPDE2D:
             self.wx, self.wy = float(p["w"][0]), float(p["w"][1])
         elif self.wkind == "var":
             self.wx, self.wy = p["w"][:self.Np], p["w"][self.Np:]
+        elif self.wkind == "cov":
+            self.lamb = float(p["w"][0])
         if self.timed:
             self.sigma = float(p["sigma"])
             if par.size > self.n_own + 1:
@@ -138,6 +145,8 @@ class SPDE2D:
         par = self._default_par(joint=self.fitQ0)
         self.data = data
         self.r = data.shape[1] if data.ndim == 2 else 1
+        if kwargs.get("ww") is not None:
+            self.ww = np.ascontiguousarray(kwargs.get("ww"), dtype="float64")
         idx = kwargs.get("idx")
         self.S = self.grid.getS(idxs=idx)
         self._set_obs(self.grid.obs_nodes(idx))
@@ -164,7 +173,9 @@ class SPDE2D:
         s = "| κ = %2.2f" % np.exp(p["kappa"]).mean() + ", γ = %2.2f" % np.exp(p["gamma"]).mean()
         if "vx" in p:
             s += ", vx = %2.2f" % np.mean(p["vx"]) + ", vy = %2.2f" % np.mean(p["vy"])
-        if self.wkind is not None:
+        if self.wkind == "cov":
+            s += ", λ = %2.2f" % p["w"][0]
+        elif self.wkind is not None:
             h = p["w"].size // 2
             s += ", wx = %2.2f" % np.mean(p["w"][:h]) + ", wy = %2.2f" % np.mean(p["w"][h:])
         if self.timed:
@@ -263,6 +274,11 @@ class SPDE2D:
         elif self.wkind == "var":
             st["ws"] = np.ascontiguousarray(g.evalAdv(p["w"]))
             aw = eng.aw_stencil(g.hx, g.hy, to_dev(st["ws"]), None, True, 3, True)
+        elif self.wkind == "cov":        # ws = lambda * ww  (cov_advection_diffusion2D.py:101)
+            if self.ww is None:
+                raise ValueError("cov-advection models need the face velocities ww (initFit(..., ww=...))")
+            st["ws"] = np.ascontiguousarray(p["w"][0] * self.ww)
+            aw = eng.aw_stencil(g.hx, g.hy, to_dev(st["ws"]), None, True, 3, False)
         st["A9"] = eng.combine_A(self.aflav if self.timed else 0, V, dt, st["kappa"], ah, aw)
         if not self.timed:
             st["Q"] = eng.atda(st["A9"], st["kappa"], V, 0)
@@ -323,6 +339,9 @@ class SPDE2D:
                 for d in (1, 2):
                     aw = eng.aw_stencil(g.hx, g.hy, wsd, None, False, d, False)
                     out.append(("dA", eng.combine_A(4, V, dt, st["kappa"], None, aw)))
+            elif self.wkind == "cov":
+                aw = eng.aw_stencil(g.hx, g.hy, to_dev(self.ww), None, True, 3, False)
+                out.append(("dA", eng.combine_A(4, V, dt, st["kappa"], None, aw)))
             else:
                 for i in range(2 * self.Np):
                     dpar = np.zeros(2 * self.Np)
@@ -461,6 +480,8 @@ class SPDE2D:
         if self.wkind == "const":
             for d in (1, 2):
                 out.append(dt * Engine.dot(GA, eng.aw_stencil(g.hx, g.hy, wsd, None, False, d, False)))
+        elif self.wkind == "cov":        # dA = Aw(ww) * dt   (cov_advection_diffusion2D.py:60,158-159)
+            out.append(dt * Engine.dot(GA, eng.aw_stencil(g.hx, g.hy, to_dev(self.ww), None, True, 3, False)))
         elif self.wkind == "var":
             if GdG is None:
                 _, GdG = eng.stencil_adjoint(g.hx, g.hy, GA, False, wsd)

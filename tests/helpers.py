@@ -59,7 +59,8 @@ def make_oracle(d):
     mod0 = None
     if g0 is not None:
         mod0 = so.OracleSPDE(spec_key(d["mod0_spde"], d["ha"], d["ani"]), g0, bc=d["bc"], par=d["mod0_par"])
-    mod = so.OracleSPDE(spec_key(d["spde"], d["ha"], d["ani"]), g, mod0=mod0, bc=d["bc"])
+    ww = d["ww"] if "ww" in d and d["ww"].size else None
+    mod = so.OracleSPDE(spec_key(d["spde"], d["ha"], d["ani"]), g, mod0=mod0, bc=d["bc"], ww=ww)
     return mod
 
 

@@ -97,6 +97,8 @@ def test_makeQ_against_reference_golden(name):
         m0 = sp.model(grid=g0, spde=d["mod0_spde"], ha=d["ha"], anisotropic=d["ani"], bc=d["bc"], parameters=d["mod0_par"])
         kw["mod0"] = m0
     mod = sp.model(grid=g, spde=d["spde"], ha=d["ha"], anisotropic=d["ani"], bc=d["bc"], **kw)
+    if "ww" in d and d["ww"].size:
+        mod.mod.ww = d["ww"]
     assert mod.mod.type == d["type"]
     Q, fac, _ = mod.mod.makeQ(d["par"], grad=False)
     Q = canon(Q)

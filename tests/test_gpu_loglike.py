@@ -18,7 +18,10 @@ def _build(d):
     kw = {}
     if g0 is not None:
         kw["mod0"] = sp.model(grid=g0, spde=d["mod0_spde"], ha=d["ha"], anisotropic=d["ani"], bc=d["bc"], parameters=d["mod0_par"])
-    return sp.model(grid=g, spde=d["spde"], ha=d["ha"], anisotropic=d["ani"], bc=d["bc"], **kw)
+    mod = sp.model(grid=g, spde=d["spde"], ha=d["ha"], anisotropic=d["ani"], bc=d["bc"], **kw)
+    if "ww" in d and d["ww"].size:
+        mod.mod.ww = d["ww"]
+    return mod
 
 
 def _dense(Q):
