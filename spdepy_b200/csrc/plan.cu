@@ -274,6 +274,15 @@ static cudaError_t launch_gemm(const Launch &L, const Program &P, const GemmSpac
     V(1, false, false) V(1, false, true) V(1, true, false) V(1, true, true)
     V(2, false, false) V(2, false, true) V(2, true, false) V(2, true, true)
 #undef V
+    // tuning-only tile shapes (NT layout), reachable through spde_gemm_single
+    if (ak == 0 && bk == 0) {
+        if (cfg == 3) return launch_gemm_variant<128, 64, 2, 2, false, false>(L, P, sp, st);    // 4 warps, 64x32 warp tiles
+        if (cfg == 4) return launch_gemm_variant<128, 128, 4, 4, false, false>(L, P, sp, st);   // 16 warps, 32x32
+        if (cfg == 5) return launch_gemm_variant<64, 128, 2, 4, false, false>(L, P, sp, st);    // 8 warps, 32x32
+        if (cfg == 6) return launch_gemm_variant<128, 128, 4, 2, false, false>(L, P, sp, st);   // 8 warps, 32x64
+        if (cfg == 7) return launch_gemm_variant<256, 64, 8, 2, false, false>(L, P, sp, st);    // 16 warps, 32x32
+        if (cfg == 8) return launch_gemm_variant<128, 64, 2, 4, false, false>(L, P, sp, st);    // 8 warps, 64x16
+    }
     return cudaErrorInvalidValue;
 }
 
@@ -776,9 +785,9 @@ extern "C" int spde_gemm_single(int cfg, int a_kmaj, int b_kmaj, int flags, int 
                                 const double *d_A, int lda, const double *d_B, int ldb, double *d_C, int ldc,
                                 int reps, float *h_ms, void *stream)
 {
-    if (cfg < 0 || cfg > 2 || M < 1 || N < 1 || K < 1) { set_error("spde_gemm_single: bad arguments"); return SPDE_ERR_ARG; }
+    if (cfg < 0 || cfg > 8 || M < 1 || N < 1 || K < 1) { set_error("spde_gemm_single: bad arguments"); return SPDE_ERR_ARG; }
     cudaStream_t st = (cudaStream_t)stream;
-    static const int BMs[3] = {128, 128, 64}, BNs[3] = {128, 64, 64};
+    static const int BMs[9] = {128, 128, 64, 128, 128, 64, 128, 256, 128}, BNs[9] = {128, 64, 64, 64, 128, 128, 128, 64, 64};
     Program P;
     GemmTask t;
     memset(&t, 0, sizeof t);

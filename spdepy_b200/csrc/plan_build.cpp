@@ -230,10 +230,12 @@ struct LevelBuilder {
     {
         int cfg = (key >> 2) - 1;
         if (cfg < 0) {
-            long long big = 0;
-            for (const Step *st : steps)
-                for (int g = st->g0; g < st->g0 + st->gn; g++) big += count_tiles(pool[g], 1);
-            cfg = big >= 2 * kSMs ? 1 : 2;
+            // Tile shape: measured on B200 (tools/tile_sweep.py, profiles/r1_tile_sweep.txt) the 64x64 tile with
+            // four warps (3-4 resident CTAs per SM) matches or beats the larger tiles on every problem shape of the
+            // schedules -- square, K = 512 panels and skinny N = 64 -- so it is used for all grouped launches.
+            const char *env = getenv("SPDE_TILE");
+            cfg = env ? atoi(env) : 2;
+            if (cfg < 0 || cfg > 2) cfg = 2;
         }
         const int variant = cfg * 4 + (key & 3);
         const int BM = CFG_BM[cfg], BN = CFG_BN[cfg];
