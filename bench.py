@@ -3,9 +3,9 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3|c2|c1] [--impl ours|reference]
 
 Metric (BASELINE.json): "loglik+grad evals/sec ... vs host-core reference".  One *step* is one
-``logLike(theta, grad=True, exact_grad=True)`` of the workload's model: assemble Q, factorise Q and
-Q + tau S^T S, logdets, conditional mean, quadratic forms, Takahashi selected inverse of both
-factors, gradient contraction.  Default workload: configs[2] of BASELINE.json (var-advection-
+``logLike(theta, grad=True, exact_grad=True)`` of the workload's model: assemble Q, factorise
+Q + tau S^T S (3-D) and the two 2-D matrices the prior's determinant collapses to, logdets, conditional
+mean, quadratic forms, Takahashi selected inverses, gradient contraction.  Default workload: configs[2] of BASELINE.json (var-advection-
 var-diffusion on the SINMOD-shaped 100x100x50 mesh, n = 5e5, 92 parameters) -- the largest config
 whose FP64 factor fits one B200; the headline 256x256x100 mesh needs a 262 GB factor (SURVEY.md
 finding 8) and is not a single-GPU configuration.
@@ -315,7 +315,10 @@ def run_ours(args):
         pms, pcnt = plan.profile(False)
         gemm_ms, gemm_launches = float(pms[0].sum()), int(pcnt[0].sum())
         total_ms = float(pms.sum())
-        alg_flops = 6.0 * stats["flops"]            # 2 factorisations (sum cc^2) + 2 Takahashi passes (2 sum cc^2 each), SURVEY 8d
+        # posterior factorisation (sum cc^2) + its Takahashi pass (2 sum cc^2); the space-time prior is
+        # collapsed to two 2-D factorisations (base.py:_prior_collapsed) whose flops are negligible and not counted
+        collapsed = bool(getattr(m, "timed", False) and getattr(m, "collapse_prior", False))
+        alg_flops = (3.0 if collapsed else 6.0) * stats["flops"]
         peak = fp64_peak()
         achieved = alg_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None
         roof = {"bound": "tensor", "kernel": "k_gemm_grouped (FP64 DMMA m8n8k4)", "achieved": achieved, "peak": peak,

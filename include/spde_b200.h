@@ -170,7 +170,10 @@ int spde_sddmm(int M, int N, int T, int bc, const double *d_X, const double *d_Y
 /* Adjoint of the assembly (transpose of spde_atda / spde_fill_spacetime): given weights W on the
  * pattern of Q, d sum(W .* Q) / d A9 (d_GA9, A9 layout), / d Qs per cell (d_Gq, Ns; Qs = kappa^2 V,
  * advection_diffusion2D.py:103) and / d Q0 (d_GQ0_25).  timed=0: W, Q in the Q25 layout and only
- * d_GA9 is produced.  d_work: 44*Ns doubles of scratch (timed only).  With these, the trace
+ * d_GA9 is produced.  timed=2: W holds weights on B = A^T (Qs/V^2) A alone (Q25 layout; the diagonal
+ * blocks of the space-time prior, whose determinant factorises over time: logdet Q = logdet Q0 +
+ * (T-1)(Ns log(1/(dt sigma)) + logdet B)); d_GA9 and d_Gq are produced, d_work: 19*Ns doubles.
+ * d_work: 44*Ns doubles of scratch (timed=1).  With these, the trace
  * sum(W .* dQ_i) of every parameter i (advection_diffusion2D.py:119-182, 204-206) is a dot
  * product with that parameter's stencil direction dA_i instead of an n x n sparse matrix. */
 int spde_assembly_adjoint(int M, int N, int T, int bc, const double *d_W, const double *d_A9,

@@ -298,7 +298,7 @@ extern "C" int spde_assembly_adjoint(int M, int N, int T, int bc, const double *
     Geo g{M, N, T, bc};
     const int Ns = M * N;
     cudaStream_t st = (cudaStream_t)stream;
-    if (timed) {
+    if (timed == 1) {
         if (!d_work || !d_GQ0_25 || !d_Gq) { set_error("spde_assembly_adjoint: work buffers required"); return SPDE_ERR_ARG; }
         double *Wd = d_work, *Wu = Wd + (size_t)25 * Ns, *Wl = Wu + (size_t)9 * Ns, *wq = Wl + (size_t)9 * Ns;
         const double cs = 1 / (dt * sigma);
@@ -306,6 +306,14 @@ extern "C" int spde_assembly_adjoint(int M, int N, int T, int bc, const double *
         SPDE_LAUNCH_CHECK();
         Geo g2{M, N, 1, bc};
         k_adj_cell<<<cdiv(Ns, 128), 128, 0, st>>>(g2, 1, Wd, Wu, Wl, wq, d_A9, d_kappa, kvar, V, cs, d_GA9, d_Gq);
+    } else if (timed == 2) {
+        // weights given directly on the pattern of B = A^T (Qs/V^2) A (Q25 layout): the time-collapsed prior,
+        // logdet Q = logdet Q0 + (T-1) (Ns log(1/(dt sigma)) + logdet B)
+        if (!d_work || !d_Gq) { set_error("spde_assembly_adjoint: work buffers required"); return SPDE_ERR_ARG; }
+        SPDE_CUDA_CHECK(cudaMemsetAsync(d_work, 0, sizeof(double) * (size_t)19 * Ns, st));
+        double *Wu = d_work, *Wl = Wu + (size_t)9 * Ns, *wq = Wl + (size_t)9 * Ns;
+        Geo g2{M, N, 1, bc};
+        k_adj_cell<<<cdiv(Ns, 128), 128, 0, st>>>(g2, 1, d_W, Wu, Wl, wq, d_A9, d_kappa, kvar, V, 1.0, d_GA9, d_Gq);
     } else {
         k_adj_cell<<<cdiv(Ns, 128), 128, 0, st>>>(g, 0, d_W, nullptr, nullptr, nullptr, d_A9, d_kappa, kvar, V, 1.0, d_GA9, d_Gq);
     }

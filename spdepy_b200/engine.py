@@ -270,6 +270,17 @@ class Engine:
                                         ptr(GQ0), _stream()))
         return GA, Gq, GQ0
 
+    def assembly_adjoint_B(self, WB, A9, kappa, V):
+        """Adjoint of ``B = A^T (Qs/V^2) A`` alone (``spde_atda`` mode 1): weights on the Q25 pattern of B ->
+        d sum(WB .* B) / d A9 and / d Qs.  Used for the time-collapsed prior log-determinant."""
+        Ns = self.Ns
+        GA = torch.empty(9 * Ns, dtype=F64, device=_dev())
+        Gq = torch.empty(Ns, dtype=F64, device=_dev())
+        work = torch.empty(19 * Ns, dtype=F64, device=_dev())
+        check(lib.spde_assembly_adjoint(self.M, self.N, 1, self.bc, ptr(WB), ptr(A9), ptr(kappa), int(kappa.numel() > 1),
+                                        V, 1.0, 1.0, 2, ptr(work), ptr(GA), ptr(Gq), None, _stream()))
+        return GA, Gq
+
     def stencil_adjoint(self, hx, hy, GA: torch.Tensor, want_H: bool, G=None):
         GH = torch.empty(8 * self.Ns, dtype=F64, device=_dev()) if want_H else None
         GdG = torch.empty(self.Ns, 4, dtype=F64, device=_dev()) if G is not None else None

@@ -296,6 +296,7 @@ class SPDE2D:
             st0 = self.mod0._state
         st["mod0"] = st0
         AtDA = eng.atda(st["A9"], st["kappa"], V, 1)
+        st["AtDA"] = AtDA
         st["Q"] = eng.fill_spacetime(AtDA, st["A9"], st["kappa"], V, st0["Q"], sigma, dt, self.divide)
         return st
 
@@ -417,13 +418,26 @@ class SPDE2D:
         return None
 
     # ------------------------------------------------------------------ gradient contraction (K11)
-    def _grad_from_weights(self, st, W):
+    def _grad_from_weights(self, st, W, prior=None):
         """sum(W .* dQ_i) for every own parameter i (and the mod0 block when fitted jointly),
-        from the adjoint of the assembly; parameter order as ``advection_diffusion2D.py:119-182``."""
+        from the adjoint of the assembly; parameter order as ``advection_diffusion2D.py:119-182``.
+        ``prior`` (space-time models): the time-collapsed prior term ``c * d logdet Q / d theta`` given as
+        ``{"c": c, "ZB": selected inverse of B, "Z0": selected inverse of Q0}``, see :meth:`_prior_collapsed`."""
         g, eng = self.grid, self.engine
         Ns = eng.Ns
         V, dt, sigma = st["V"], st["dt"], st["sigma"]
         GA, Gq, GQ0 = eng.assembly_adjoint(W, st["A9"], st["kappa"], V, sigma, dt, self.timed)
+        s_q0 = Engine.dot(GQ0, st["mod0"]["Q"]) if self.timed else 0.0
+        s_prior_sigma = 0.0
+        if prior is not None:
+            # c*logdet Q = c*logdet Q0 + c*(T-1) (logdet B - Ns log(dt sigma)): weights c (T-1) Z_B on B, c Z_0 on Q0
+            c = prior["c"]
+            GA2, Gq2 = self.engine2d.assembly_adjoint_B(prior["ZB"] * (c * (eng.T - 1)), st["A9"], st["kappa"], V)
+            GA = GA + GA2
+            Gq = Gq + Gq2
+            if prior.get("Z0") is not None:
+                GQ0 = GQ0 + c * prior["Z0"]
+            s_prior_sigma = -c * (eng.T - 1) * Ns
         out = []
         # kappa
         kap = st["kappa"]
@@ -491,8 +505,7 @@ class SPDE2D:
         if self.timed:
             # log sigma: dQ = -(Q - blockdiag(Q0-part))   (advection_diffusion2D.py:170-175)
             s_total = Engine.dot(W, st["Q"])
-            s_q0 = Engine.dot(GQ0, st["mod0"]["Q"])
-            out.append(-(s_total - s_q0))
+            out.append(-(s_total - s_q0) + s_prior_sigma)
             if st["joint"]:
                 out.extend(self.mod0._grad_from_weights(st["mod0"], GQ0))
         return out
@@ -516,6 +529,36 @@ class SPDE2D:
             self._bs_cache = to_dev(np.ascontiguousarray(self.grid.bs))
         return self._bs_cache
 
+    # ------------------------------------------------------------------ time-collapsed prior
+    collapse_prior = True    # False: factorise the 3-D prior precision as the reference does (validation)
+
+    @property
+    def engine2d(self) -> Engine:
+        """Engine of one time slice (the 5x5 pattern of B = A^T (Qs/V^2) A)."""
+        return Engine.get(self.engine.M, self.engine.N, 1, self.bc)
+
+    def _prior_collapsed(self, st, want_grad):
+        """logdet of the space-time prior and the selected inverses that carry its gradient, from two 2-D
+        factorisations.  The prior of ``advection_diffusion2D.py:112-116`` is ``Q = blockdiag(Q0, 0, ...) +
+        c G^T G`` with ``c = 1/(dt sigma)`` and ``G`` block bidiagonal (rows ``[-Qs^1/2, Qs^1/2 V^-1 A]``), so
+
+            logdet Q = logdet Q0 + (T-1) (Ns log c + logdet B),    B = A^T (Qs/V^2) A  (``spde_atda`` mode 1),
+
+        and ``tr(Q^-1 dQ_i) = tr(Q0^-1 dQ0_i) + (T-1) (tr(B^-1 dB_i) - Ns dlog(sigma)_i)``."""
+        e2, e0 = self.engine2d, self.mod0.engine
+        T, Ns = self.engine.T, self.engine.Ns
+        # store 1 of the slice engine holds B, store 0 of mod0's engine holds Q0 (the two may be one engine)
+        e0.factorize_async(0, st["mod0"]["Q"])
+        e2.factorize_async(1, st["AtDA"])
+        e0.factor_wait(0)
+        e2.factor_wait(1)
+        ld0, ldB = e0.logdet(0), e2.logdet(1)
+        out = {"logdet": ld0 + (T - 1) * (ldB - Ns * np.log(st["dt"] * st["sigma"])), "logdetQ0": ld0, "logdetB": ldB}
+        if want_grad:
+            out["ZB"] = e2.selinv(1)
+            out["Z0"] = e0.selinv(0) if st["joint"] else None
+        return out
+
     # ------------------------------------------------------------------ likelihood (advection_diffusion2D.py:187-223)
     def logLike(self, par, nh1=100, grad=True, probes=None, exact_grad=False):
         eng = self.engine
@@ -531,11 +574,22 @@ class SPDE2D:
         st = self._assemble(par)
         self._state = st
         Q = st["Q"]
-        eng.factorize_async(0, Q)               # the two factorisations run concurrently
-        eng.factorize_async(1, Q, cnt, tau)
-        eng.factor_wait(0)
-        eng.factor_wait(1)
-        ldQ = eng.logdet(0)
+        # space-time prior: its determinant (and hence every prior trace of the gradient) factorises over
+        # time into 2-D problems, so only the posterior precision needs the 3-D factorisation.  The
+        # Hutchinson estimator solves with Q itself and keeps the 3-D factor of the prior.
+        collapsed = self.timed and self.collapse_prior and (exact_grad or not grad)
+        if collapsed:
+            eng.factorize_async(1, Q, cnt, tau)
+            prior = self._prior_collapsed(st, want_grad=grad)
+            eng.factor_wait(1)
+            ldQ = prior["logdet"]
+        else:
+            prior = None
+            eng.factorize_async(0, Q)               # the two factorisations run concurrently
+            eng.factorize_async(1, Q, cnt, tau)
+            eng.factor_wait(0)
+            eng.factor_wait(1)
+            ldQ = eng.logdet(0)
         ldQc = eng.logdet(1)
         mu_c = eng.solve(1, eng.scatter_obs(data, obs, tau))          # Q_c^-1 S^T data tau
         quad = Engine.dot(mu_c, eng.q_apply(Q, mu_c))
@@ -544,7 +598,13 @@ class SPDE2D:
         self.last = {"mu_c": mu_c, "logdetQ": ldQ, "logdetQc": ldQc, "quad": quad, "resid": resid}
         if not grad:
             return -like / (nobs * r)
-        if exact_grad:
+        if exact_grad and collapsed:
+            W = eng.selinv(1)
+            nd = eng.nslots // 2
+            tr_tau = Engine.dot(cnt, W[nd * eng.n:(nd + 1) * eng.n]) * tau
+            W *= -0.5 * r
+            prior["c"] = 0.5 * r
+        elif exact_grad:
             Z, Zc = eng.selinv_pair()
             nd = eng.nslots // 2
             tr_tau = Engine.dot(cnt, Zc[nd * eng.n:(nd + 1) * eng.n].contiguous()) * tau
@@ -563,7 +623,7 @@ class SPDE2D:
             tr_tau = Engine.wdot(TrQc, Vp, cnt) * tau / nh1
         W = eng.sddmm(mu_c, mu_c, -0.5, W)
         g_par = np.zeros(par.size)
-        gi = self._grad_from_weights(st, W)
+        gi = self._grad_from_weights(st, W, prior)
         g_par[:len(gi)] = gi
         g_par[-1] = nobs * r / 2 - 1 / 2 * tr_tau * r - tau / 2 * resid
         return -like / (nobs * r), -g_par / (nobs * r)
