@@ -46,7 +46,12 @@ WORKLOADS = {
            "advection-diffusion 50x50x20, 5000 obs (configs[1])"),
     "c3": ("var-advection-var-diffusion", "var-whittle-matern", False, True, 1, 100, 100, 50,
            "var-advection-var-diffusion 100x100x50 SINMOD-shaped, 92 parameters, 10% obs (configs[2])"),
+    # batched sweep: every step is one theta-evaluation (likelihood + exact gradient) PLUS 1024 prior samples at that
+    # theta (3-D factor of Q, 1024-column back substitution); thetas are sharded over the ranks
+    "c5": ("var-advection-var-diffusion", "var-whittle-matern", False, True, 1, 100, 100, 50,
+           "batched sweep on 100x100x50: per theta logLike+exact gradient and 1024 samples, thetas sharded over the GPUs (configs[4])"),
 }
+N_SAMPLES = {"c5": 1024}
 
 
 def make_inputs(name, M=None, N=None, T=None, seed=0):
@@ -54,7 +59,7 @@ def make_inputs(name, M=None, N=None, T=None, seed=0):
     with the same cell size, for the bounded CPU sample)."""
     spde, spde0, ha, ani, bc, M0, N0, T0, _ = WORKLOADS[name]
     M, N, T = M or M0, N or N0, (T or T0) if T0 else None
-    if name == "c3":
+    if name in ("c3", "c5"):
         x, y, t = 800.0 * np.arange(M), 800.0 * np.arange(N), 10.0 * np.arange(T)
         theta = np.load(os.path.join(ROOT, "tests", "golden", "c3_theta.npy"))
         p0 = np.hstack([theta[55:91], theta[-1]])
@@ -109,7 +114,7 @@ def cpu_reference(name, full_stats, budget_s=25.0, nh1=100):
     import spde_oracle as so
     from spdepy_b200 import _lib
     spde, spde0, ha, ani, bc, M0, N0, T0, _ = WORKLOADS[name]
-    if name == "c3":
+    if name in ("c3", "c5"):
         M, N, T = 24, 24, 10
     elif name == "c2":
         M, N, T = 30, 30, 12
@@ -152,6 +157,9 @@ def cpu_reference(name, full_stats, budget_s=25.0, nh1=100):
     full_fac = min(t_fac * full_stats["flops"] / s["flops"], full_stats["flops"] / (host_gflops * 1e9))
     full_solve = min(t_solve * full_stats["nnzL"] / s["nnzL"], 4.0 * full_stats["nnzL"] * 2 * nh1 / (host_gflops * 1e9))
     full_t = full_asm + 2 * full_fac + full_solve
+    nsamp = N_SAMPLES.get(name, 0)
+    if nsamp:      # one more factorisation is already counted (makeQ); add the nsamp-column back substitution
+        full_t += 2.0 * full_stats["nnzL"] * nsamp / (host_gflops * 1e9)
     return {
         "value": 1.0 / full_t, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
         "sample": ("oracle port (SciPy assembly + supernodal Cholesky on LAPACK, Hutchinson nh1=%d as the reference does) of "
@@ -260,6 +268,10 @@ def run_ours(args):
     npar = inp["theta"].size
     red = torch.zeros(npar + 1, dtype=torch.float64, device="cuda")
 
+    nsamp = N_SAMPLES.get(name, 0)
+    gen = torch.Generator(device="cuda").manual_seed(8 + rank)
+    sample_chk = [None]
+
     def step(theta, resident):
         if resident:
             if "data" not in m._obs:
@@ -268,6 +280,16 @@ def run_ours(args):
             m._obs.pop("data", None)
             m.data = pinned_data.numpy()
         like, jac = m.logLike(theta, grad=True, exact_grad=True)
+        if nsamp:
+            # Model.sample at this theta (model.py:73-87): x = P^T L^-T z with L the factor of the 3-D prior
+            eng = m.engine
+            eng.factorize(0, m._state["Q"])
+            chk = 0.0
+            for c0 in range(0, nsamp, 512):
+                z = torch.randn(eng.n, min(512, nsamp - c0), dtype=torch.float64, device="cuda", generator=gen)
+                x = eng.solve(0, z, 10)
+                chk += float((x * x).sum())
+            sample_chk[0] = chk / (eng.n * nsamp)
         if world > 1:
             red[0] = like
             red[1:] = torch.as_tensor(jac, device="cuda")
@@ -361,6 +383,9 @@ def run_ours(args):
             "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
             "last_like": float(last[0]),
         }
+        if nsamp:
+            line["config"]["samples_per_theta"] = nsamp
+            line["mean_sample_variance"] = sample_chk[0]
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
@@ -398,7 +423,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))   # c5 = batched sweep (configs[4])
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()

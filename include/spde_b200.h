@@ -196,6 +196,11 @@ int spde_gemm_single(int cfg, int a_kmaj, int b_kmaj, int flags, int M, int N, i
                      const double *d_A, int lda, const double *d_B, int ldb, double *d_C, int ldc,
                      int reps, float *h_ms, void *stream);
 
+/* Latency probe of the 64x64 POTRF + inverse kernel that sits on the critical path of every front: `ntasks`
+ * synthetic SPD blocks of order b, `reps` launches.  *h_us = mean microseconds per launch; h_clk[5] = SM clock
+ * of CTA 0 at entry / after the load / after the column sweep / after the block inversion / at exit. */
+int spde_potrf_bench(int b, int ld, int ntasks, int reps, float *h_us, long long *h_clk, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

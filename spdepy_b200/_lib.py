@@ -73,6 +73,7 @@ _SIGS = {
                                  c_int, ctypes.POINTER(ctypes.c_float), c_vp]),
     "spde_stencil_adjoint": (c_int, [c_int, c_int, c_int, c_dbl, c_dbl, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "spde_gemv_t": (c_int, [c_vp, c_vp, c_int, c_int, c_vp, c_vp]),
+    "spde_potrf_bench": (c_int, [c_int, c_int, c_int, c_int, ctypes.POINTER(ctypes.c_float), c_vp, c_vp]),
 }
 
 EXPORTS = tuple(_SIGS)

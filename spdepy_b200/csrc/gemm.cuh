@@ -46,6 +46,15 @@ struct GemmSpaces {
 
 struct TileRef { int task, ti, tj, pad; };
 
+// Programmatic dependent launch (sm_90+): every kernel of a schedule lets its successor start launching
+// at once and then waits for its predecessor to complete and flush.  The wait is unconditional and first,
+// so completion order stays transitive along the chain (a grid never completes before its predecessor).
+__device__ __forceinline__ void pdl_enter()
+{
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem, int src_bytes)
 {
     unsigned s = (unsigned)__cvta_generic_to_shared(smem);
@@ -126,6 +135,7 @@ k_gemm_grouped(const GemmTask *__restrict__ tasks, const TileRef *__restrict__ t
     double *sA = smem;
     double *sB = smem + GEMM_STAGES * A_ELEMS;
 
+    pdl_enter();
     const TileRef tr = tiles[blockIdx.x];
     const GemmTask tk = tasks[tr.task];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -274,6 +284,7 @@ __global__ void __launch_bounds__(256) k_gemv_grouped(const GemmTask *__restrict
 {
     constexpr int KC = B_KMAJ ? GEMV_KC_K : GEMV_KC_N;
     __shared__ double sA[4][KC];             // the right-hand-side slice of this K chunk (<= 4 columns)
+    pdl_enter();
     const TileRef tr = tiles[blockIdx.x];
     const GemmTask tk = tasks[tr.task];
     const int tid = threadIdx.x;

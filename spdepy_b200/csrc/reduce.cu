@@ -136,6 +136,25 @@ __global__ void k_sddmm(Geo g, const double *__restrict__ X, const double *__res
     }
 }
 
+// single-column case (the -1/2 mu mu^T term of every gradient): one thread per node, slot loop unrolled by the
+// compiler, every slot one coalesced read-modify-write stream
+__global__ void k_sddmm1(Geo g, const double *__restrict__ X, const double *__restrict__ Y, double alpha,
+                         int accumulate, double *__restrict__ W)
+{
+    const long long n = (long long)g.M * g.N * g.T;
+    const int ns = g.nslots();
+    for (long long node = (long long)blockIdx.x * blockDim.x + threadIdx.x; node < n; node += (long long)gridDim.x * blockDim.x) {
+        const double x = alpha * X[node];
+        for (int q = 0; q < ns; q++) {
+            const int c = g.slot_nbr((int)node, q);
+            const long long o = (long long)q * n + node;
+            if (c < 0) { if (!accumulate) W[o] = 0.0; continue; }
+            const double v = x * Y[c];
+            W[o] = accumulate ? W[o] + v : v;
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // adjoint of the assembly.  Phase 1 (space-time only): sums of W over the time blocks.
 //   Wd[q][k] = sum_{t>=1} W[9+q][(k,t)]      weights of A^T d A
@@ -283,8 +302,12 @@ extern "C" int spde_sddmm(int M, int N, int T, int bc, const double *d_X, const 
 {
     Geo g{M, N, T, bc};
     const long long n = (long long)M * N * T;
-    const long long blocks = std::min<long long>((n * 32 + 255) / 256, 148 * 16);
-    k_sddmm<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(g, d_X, d_Y, k, alpha, accumulate, d_W);
+    if (k == 1) {
+        k_sddmm1<<<(int)std::min<long long>((n + 255) / 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(g, d_X, d_Y, alpha, accumulate, d_W);
+    } else {
+        const long long blocks = std::min<long long>((n * 32 + 255) / 256, 148 * 16);
+        k_sddmm<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(g, d_X, d_Y, k, alpha, accumulate, d_W);
+    }
     SPDE_LAUNCH_CHECK();
     count_launch();
     return SPDE_OK;

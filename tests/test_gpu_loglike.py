@@ -147,3 +147,47 @@ def test_lazy_dQ_operators_vs_oracle(name):
         got = dQ[i] @ X
         assert np.abs(got - ref).max() <= 1e-9 * max(np.abs(ref).max(), 1e-300), (i, np.abs(got - ref).max(), np.abs(ref).max())
     assert abs(dQ[0].tocsc() - dQo[0]).max() <= 1e-9 * abs(dQo[0]).max()
+
+
+@pytest.mark.parametrize("name,two", [("wm_ani_bc1_ext", True), ("ad_ani_bc3_q0", False)])
+def test_bordered_model_with_regression_columns(name, two):
+    """Model.setModel(useCov=True) / update / sample (model.py:73-87,120-153): the latent vector gains regression
+    coefficients and the precision a dense border.  Checked against a dense solve of the bordered system and a dense
+    Cholesky under the build's permutation (border ordered last)."""
+    d = load_golden(name)
+    mod = _build(d)
+    mod.mod.setQ(d["par"])
+    g = mod.grid
+    nobs_all = g.M * g.N * g.T
+    rng = np.random.default_rng(11)
+    cov = rng.uniform(0.5, 2.0, size=nobs_all)
+    if two:
+        mod.setModel(mu=cov, sigmas=np.log(np.array([0.01, 140.0])), useCov=True, scale=True)
+        k = 2
+    else:
+        mod.setModel(mu=np.zeros(nobs_all), sigmas=np.log(0.5), useCov=True)
+        k = 1
+    n = mod.mod.engine.n
+    S = g.getS()
+    assert S.shape == (nobs_all, n + k) and mod.mu.shape == (n + k,)
+    Q0 = mod.getQ().toarray()
+    assert Q0.shape == (n + k, n + k)
+    mu0 = mod.mu.copy()
+    idx = d["idx"][: max(10, d["idx"].size // 2)]
+    y = rng.normal(size=idx.size)
+    tau = 3.0
+    mod.update(y=y, idx=idx, tau=tau)
+    Si = g.getS(idx).toarray()
+    Qd = Q0 + tau * Si.T @ Si
+    mu_ref = mu0 + np.linalg.solve(Qd, Si.T @ (y - Si @ mu0)) * tau
+    assert relerr(mod.mu, mu_ref) < 1e-9
+    assert relerr(mod.getQ().toarray(), Qd) < 1e-12
+    # samples: x = P_aug^T L_aug^-T z + mu with the border ordered last
+    X = mod.sample(n=3, seed=5, simple=True)
+    perm = np.concatenate([mod.mod.engine.plan.perm.astype(np.int64), n + np.arange(k)])
+    L = np.linalg.cholesky(Qd[np.ix_(perm, perm)])
+    z = np.random.default_rng(5).normal(size=(n + k) * 3).reshape(n + k, 3)
+    x = np.empty_like(z)
+    x[perm] = np.linalg.solve(L.T, z)
+    ref = S.toarray() @ (x + mod.mu[:, None])
+    assert relerr(X, ref) < 1e-9
