@@ -65,14 +65,14 @@ __global__ void k_extend_add(const ExtTask *__restrict__ tasks, const TileRef *_
 
 // ---------------------------------------------------------------------------------------------
 // POTRF of one diagonal block (b <= 64) in shared memory + explicit inverse of the factor.
-// One CTA of 1024 threads per block.  This kernel sits on the critical path of every front (one launch
-// per 64 pivot columns), so it is organised for latency:
-//   * right-looking column sweep, one barrier per column, 16 threads per row so that no thread updates
-//     more than four elements per column;
+// One CTA of 512 threads per block.  This kernel sits on the critical path of every front (one launch
+// per 64 pivot columns), so it is organised for latency (tools/potrf_probe.py gives the phase clocks):
+//   * right-looking column sweep, one barrier per column, 8 threads per row, four independent updates in
+//     flight per thread; the loop body is kept short because with many warps the sweep is issue-bound;
 //   * W = L^-1 by recursive block inversion, inv([[A,0],[B,C]]) = [[A^-1,0],[-C^-1 B A^-1, C^-1]]: eight
 //     8x8 triangular inverses by substitution (one thread per column, column kept in registers), then three
 //     doubling levels of two small dense products each -- 7 barriers instead of a 63-step substitution.
-constexpr int POTRF_THREADS = 1024;
+constexpr int POTRF_THREADS = 512;
 template <bool BENCH>
 __global__ void __launch_bounds__(POTRF_THREADS) k_potrf_t(const PotrfTask *__restrict__ tasks, double *__restrict__ L,
                                                            double *__restrict__ dinv, int *__restrict__ status,
@@ -97,37 +97,43 @@ __global__ void __launch_bounds__(POTRF_THREADS) k_potrf_t(const PotrfTask *__re
     __syncthreads();
     POTRF_MARK(1);
     {
-        const int i = tid & 63, ty = tid >> 6;      // row, column group (16 groups)
+        // rows i = tid % 64; the threads of a row split its columns c = j+1+ty, +G, ... (G column groups)
+        constexpr int G = POTRF_THREADS / NB;
+        const int i = tid & 63, ty = tid >> 6;
+        double *ai = &a[i][0];
         for (int j = 0; j < b; j++) {
             const double d = a[j][j];
             const bool ok = d > 0.0;
             const double inv = ok ? rsqrt(d) : nan("");     // 1/l_jj; l_jj = d * inv
             const bool mine = i > j && i < b;
-            const double li = mine ? a[i][j] * inv : 0.0;
+            double li = 0.0;
             if (mine) {
-                // a[i][c] -= l_ic * l_cj for c = j+1+ty, +16, ... <= i: at most four independent updates
-                const int c0 = j + 1 + ty;
-                double p[4], q[4];
+                li = ai[j] * inv;
+                // four independent updates in flight per round (loads first, then the dependent arithmetic)
+                for (int c0 = j + 1 + ty; c0 <= i; c0 += 4 * G) {
+                    double p[4], q[4];
 #pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    const int c = c0 + 16 * u;
-                    p[u] = c <= i ? a[c][j] : 0.0;
-                    q[u] = c <= i ? a[i][c] : 0.0;
-                }
+                    for (int u = 0; u < 4; u++) {
+                        const int c = c0 + G * u;
+                        p[u] = c <= i ? a[c][j] : 0.0;
+                        q[u] = c <= i ? ai[c] : 0.0;
+                    }
 #pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    const int c = c0 + 16 * u;
-                    if (c <= i) a[i][c] = q[u] - li * (p[u] * inv);
+                    for (int u = 0; u < 4; u++) {
+                        const int c = c0 + G * u;
+                        if (c <= i) ai[c] = q[u] - li * (p[u] * inv);
+                    }
                 }
             }
             __syncthreads();                       // column j has been read by everyone
-            if (ty == 0 && mine) a[i][j] = li;
-            if (tid == 0) { a[j][j] = d * inv; if (!ok && bad < 0) bad = j; }
+            if (ty == 0 && mine) ai[j] = li;
+            if (tid == 0) { a[j][j] = d * inv; wd[j] = inv; if (!ok && bad < 0) bad = j; }
         }
+        if (tid >= b && tid < NB) wd[tid] = 0.0;
         __syncthreads();
     }
     POTRF_MARK(2);
-    // ---- W = L^-1.  W(i,c) for i > c lives at a[c][i]; diag(W) in wd.
+    // ---- W = L^-1.  W(i,c) for i > c lives at a[c][i]; diag(W) = 1/l_ii is already in wd.
     if (tid < NB) {
         // level 0: 8x8 diagonal blocks, thread = (block, column), the column stays in registers
         const int o = tid & ~7, c = tid & 7;
@@ -138,19 +144,17 @@ __global__ void __launch_bounds__(POTRF_THREADS) k_potrf_t(const PotrfTask *__re
 #pragma unroll
             for (int i = 0; i < 8; i++) {
                 if (i < c || o + i >= b) continue;
-                if (i == c) { w[i] = 1.0 / a[o + i][o + i]; continue; }
+                if (i == c) { w[i] = wd[o + i]; continue; }
                 double sum = 0.0;
 #pragma unroll
                 for (int k = 0; k < 8; k++)
                     if (k >= c && k < i) sum += a[o + i][o + k] * w[k];
-                w[i] = -sum / a[o + i][o + i];
+                w[i] = -sum * wd[o + i];
             }
         }
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
-            if (i == c) wd[tid] = w[i];
+        for (int i = 0; i < 8; i++)
             if (i > c) a[o + c][o + i] = w[i];
-        }
     }
     __syncthreads();
 #pragma unroll 1
@@ -161,23 +165,29 @@ __global__ void __launch_bounds__(POTRF_THREADS) k_potrf_t(const PotrfTask *__re
         for (int e = tid; e < total; e += POTRF_THREADS) {      // T = B * W_A
             const int pr = e / per, r = e - pr * per, i = r / s, c = r - i * s;
             const int o = pr * 2 * s;
-            double sum = 0.0;
+            double s0 = 0.0, s1 = 0.0;
             if (o + s + i < b) {
-                sum = a[o + s + i][o + c] * wd[o + c];
-                for (int k = c + 1; k < s; k++) sum += a[o + s + i][o + k] * a[o + c][o + k];
+                const double *bi = &a[o + s + i][o], *wc = &a[o + c][o];
+                s0 = bi[c] * wd[o + c];
+                int k = c + 1;
+                for (; k + 1 < s; k += 2) { s0 += bi[k] * wc[k]; s1 += bi[k + 1] * wc[k + 1]; }
+                if (k < s) s0 += bi[k] * wc[k];
             }
-            tmp[e] = sum;
+            tmp[e] = s0 + s1;
         }
         __syncthreads();
         for (int e = tid; e < total; e += POTRF_THREADS) {      // W21 = -W_C * T
             const int pr = e / per, r = e - pr * per, i = r / s, c = r - i * s;
             const int o = pr * 2 * s, oc = o + s;
-            double sum = 0.0;
+            double s0 = 0.0, s1 = 0.0;
             if (oc + i < b) {
-                sum = wd[oc + i] * tmp[pr * per + i * s + c];
-                for (int k = 0; k < i; k++) sum += a[oc + k][oc + i] * tmp[pr * per + k * s + c];
+                const double *tc = &tmp[pr * per + c];
+                s0 = wd[oc + i] * tc[i * s];
+                int k = 0;
+                for (; k + 1 < i; k += 2) { s0 += a[oc + k][oc + i] * tc[k * s]; s1 += a[oc + k + 1][oc + i] * tc[(k + 1) * s]; }
+                if (k < i) s0 += a[oc + k][oc + i] * tc[k * s];
             }
-            a[o + c][oc + i] = -sum;
+            a[o + c][oc + i] = -(s0 + s1);
         }
         __syncthreads();
     }
@@ -498,13 +508,17 @@ static int join_store(Plan &p, int which, cudaStream_t st)
     if (p.pending[which]) {
         SPDE_CUDA_CHECK(cudaStreamWaitEvent(st, p.ev_out[which], 0));
         p.pending[which] = false;
+        p.pending_readonly[which] = false;
     }
     return SPDE_OK;
 }
 
-static int run_program(Plan &p, Program &P, int which, cudaStream_t st, double *d_Zq, bool defer_join = false)
+// lane 0: factorisation / Takahashi (private stream cap_stream, join may be deferred); lane 1: triangular solves
+// (private stream solve_stream, always joined before returning; skips the join with an in-flight read-only graph)
+static int run_program(Plan &p, Program &P, int which, cudaStream_t st, double *d_Zq, bool defer_join = false, int lane = 0)
 {
-    int rc = join_store(p, which, st);
+    int rc = SPDE_OK;
+    if (lane == 0 || !p.pending_readonly[which]) rc = join_store(p, which, st);
     if (rc) return rc;
     if (p.prof_on || !p.use_graphs) return issue_program(p, P, which, st, d_Zq);
     GemmSpaces sp = spaces_of(p, which);
@@ -520,7 +534,12 @@ static int run_program(Plan &p, Program &P, int which, cudaStream_t st, double *
         SPDE_CUDA_CHECK(cudaEventCreateWithFlags(&p.ev_in[which], cudaEventDisableTiming));
         SPDE_CUDA_CHECK(cudaEventCreateWithFlags(&p.ev_out[which], cudaEventDisableTiming));
     }
-    cudaStream_t cs = p.cap_stream[which];
+    if (lane == 1 && !p.solve_stream[which]) {
+        SPDE_CUDA_CHECK(cudaStreamCreateWithFlags(&p.solve_stream[which], cudaStreamNonBlocking));
+        SPDE_CUDA_CHECK(cudaEventCreateWithFlags(&p.sev_in[which], cudaEventDisableTiming));
+        SPDE_CUDA_CHECK(cudaEventCreateWithFlags(&p.sev_out[which], cudaEventDisableTiming));
+    }
+    cudaStream_t cs = lane ? p.solve_stream[which] : p.cap_stream[which];
     if (!P.graph[which]) {
         if (P.runs[which]++ == 0) return issue_program(p, P, which, st, d_Zq);   // warm run: uploads, lazy init
         SPDE_CUDA_CHECK(cudaStreamBeginCapture(cs, cudaStreamCaptureModeRelaxed));
@@ -535,14 +554,23 @@ static int run_program(Plan &p, Program &P, int which, cudaStream_t st, double *
         cudaGraphDestroy(g);
         P.graph_key[which] = key;
     }
+    int nk = 0;
+    for (const Launch &L : P.launches) nk += L.kind != LK_ZERO;
+    count_launch(nk);
+    if (lane == 1) {
+        SPDE_CUDA_CHECK(cudaEventRecord(p.sev_in[which], st));
+        SPDE_CUDA_CHECK(cudaStreamWaitEvent(cs, p.sev_in[which], 0));
+        SPDE_CUDA_CHECK(cudaGraphLaunch(P.graph[which], cs));
+        SPDE_CUDA_CHECK(cudaEventRecord(p.sev_out[which], cs));
+        SPDE_CUDA_CHECK(cudaStreamWaitEvent(st, p.sev_out[which], 0));
+        return SPDE_OK;
+    }
     SPDE_CUDA_CHECK(cudaEventRecord(p.ev_in[which], st));
     SPDE_CUDA_CHECK(cudaStreamWaitEvent(cs, p.ev_in[which], 0));
     SPDE_CUDA_CHECK(cudaGraphLaunch(P.graph[which], cs));
     SPDE_CUDA_CHECK(cudaEventRecord(p.ev_out[which], cs));
     p.pending[which] = true;
-    int nk = 0;
-    for (const Launch &L : P.launches) nk += L.kind != LK_ZERO;
-    count_launch(nk);
+    p.pending_readonly[which] = (&P == &p.selinv);
     return defer_join ? SPDE_OK : join_store(p, which, st);
 }
 
@@ -611,6 +639,7 @@ extern "C" void spde_plan_destroy(spde_plan *pp)
         cudaFree(p->d_L[a]); cudaFree(p->d_dinv[a]); cudaFree(p->d_ybuf[a]); cudaFree(p->d_zq[a]);
         for (int b = 0; b < 2; b++) { cudaFree(p->d_arena[a][b]); cudaFree(p->d_zarena[a][b]); }
         if (p->cap_stream[a]) { cudaStreamDestroy(p->cap_stream[a]); cudaEventDestroy(p->ev_in[a]); cudaEventDestroy(p->ev_out[a]); }
+        if (p->solve_stream[a]) { cudaStreamDestroy(p->solve_stream[a]); cudaEventDestroy(p->sev_in[a]); cudaEventDestroy(p->sev_out[a]); }
     }
     cudaFree(p->d_X); cudaFree(p->d_red); cudaFree(p->d_idx); cudaFree(p->d_qdest);
     cudaFree(p->d_diagpos); cudaFree(p->d_cand); cudaFree(p->d_perm); cudaFree(p->d_status); cudaFree(p->d_zentries);
@@ -800,7 +829,7 @@ extern "C" int spde_solve(spde_plan *pp, int which, int mode, double *d_X, int k
     Plan &p = *reinterpret_cast<Plan *>(pp);
     if (!p.factored[which] || k < 1 || mode < 1 || mode > 15 || !(mode & 3)) { set_error("spde_solve: bad state/arguments"); return SPDE_ERR_ARG; }
     cudaStream_t st = (cudaStream_t)stream;
-    { int rcj = join_store(p, which, st); if (rcj) return rcj; }
+    if (!p.pending_readonly[which]) { int rcj = join_store(p, which, st); if (rcj) return rcj; }
     const int n = p.sym.n, kp = k + (k & 1);
     const int64_t need = (int64_t)n * kp;
     if (p.x_cap < need) {
@@ -815,8 +844,8 @@ extern "C" int spde_solve(spde_plan *pp, int which, int mode, double *d_X, int k
     k_perm_in<<<grid, 256, 0, st>>>(d_X, p.d_perm, n, k, kp, (mode >> 2) & 1, p.d_X);
     SPDE_LAUNCH_CHECK();
     int rc;
-    if (mode & 1) { rc = run_program(p, p.solve_program(k, 0), which, st, nullptr); if (rc) return rc; }
-    if (mode & 2) { rc = run_program(p, p.solve_program(k, 1), which, st, nullptr); if (rc) return rc; }
+    if (mode & 1) { rc = run_program(p, p.solve_program(k, 0), which, st, nullptr, false, 1); if (rc) return rc; }
+    if (mode & 2) { rc = run_program(p, p.solve_program(k, 1), which, st, nullptr, false, 1); if (rc) return rc; }
     k_perm_out<<<grid, 256, 0, st>>>(p.d_X, p.d_perm, n, k, kp, (mode >> 3) & 1, d_X);
     SPDE_LAUNCH_CHECK();
     return SPDE_OK;

@@ -109,6 +109,11 @@ struct Plan {
     cudaStream_t cap_stream[2] = {nullptr, nullptr};
     cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
     bool pending[2] = {false, false};   // a graph of this store is in flight and not yet joined with the caller's stream
+    bool pending_readonly[2] = {false, false};   // ... and it only READS the factor (Takahashi): solves may run beside it
+    // second lane for the triangular solves, so that the latency-bound k = 1 solve of the conditional mean overlaps
+    // the Takahashi pass of the same store
+    cudaStream_t solve_stream[2] = {nullptr, nullptr};
+    cudaEvent_t sev_in[2] = {nullptr, nullptr}, sev_out[2] = {nullptr, nullptr};
     double *d_zq[2] = {nullptr, nullptr};
     int sel_ready[2] = {0, 0};
     // optional per-launch timing (CUDA events), accumulated per (launch kind, GEMM variant)

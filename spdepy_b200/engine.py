@@ -197,6 +197,16 @@ class Engine:
         check(lib.spde_selinv_fetch(self.plan.h, 1, ptr(Zc), _stream()))
         return Z, Zc
 
+    def selinv_start(self, which: int) -> None:
+        """Enqueue the Takahashi pass of a store on its private stream; solves with the same store may run beside
+        it (both only read the factor).  Pair with :meth:`selinv_fetch`."""
+        check(lib.spde_selinv_start(self.plan.h, which, _stream()))
+
+    def selinv_fetch(self, which: int) -> torch.Tensor:
+        Z = torch.empty(self.nslots * self.n, dtype=F64, device=_dev())
+        check(lib.spde_selinv_fetch(self.plan.h, which, ptr(Z), _stream()))
+        return Z
+
     def logdet(self, which: int) -> float:
         out = ctypes.c_double()
         check(lib.spde_logdet(self.plan.h, which, ctypes.byref(out), _stream()))

@@ -591,6 +591,9 @@ class SPDE2D:
             eng.factor_wait(1)
             ldQ = eng.logdet(0)
         ldQc = eng.logdet(1)
+        overlap = grad and exact_grad and collapsed
+        if overlap:
+            eng.selinv_start(1)     # the Takahashi pass runs beside the (latency-bound) solve and reductions below
         mu_c = eng.solve(1, eng.scatter_obs(data, obs, tau))          # Q_c^-1 S^T data tau
         quad = Engine.dot(mu_c, eng.q_apply(Q, mu_c))
         resid = Engine.residual_ss(data, mu_c, obs)
@@ -599,7 +602,7 @@ class SPDE2D:
         if not grad:
             return -like / (nobs * r)
         if exact_grad and collapsed:
-            W = eng.selinv(1)
+            W = eng.selinv_fetch(1)
             nd = eng.nslots // 2
             tr_tau = Engine.dot(cnt, W[nd * eng.n:(nd + 1) * eng.n]) * tau
             W *= -0.5 * r

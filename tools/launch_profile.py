@@ -53,6 +53,13 @@ for prog, pname in ((0, "factor"), (3, "selinv")):
         if msk.any():
             print("   class %-12s launches %5d  ms %9.2f  flop %.3g  -> %.2f TFLOP/s" % (lab, msk.sum(), rows[msk, 0].sum(), rows[msk, 1].sum(),
                                                                                          rows[msk, 1].sum() / max(rows[msk, 0].sum(), 1e-9) / 1e9))
+    # efficiency against machine fill: tiles per launch relative to the 592 resident CTAs (148 SMs x 4)
+    for lo, hi in ((0, 148), (148, 592), (592, 1776), (1776, 5920), (5920, 1 << 30)):
+        msk = (rows[:, 2] >= lo) & (rows[:, 2] < hi)
+        if msk.any():
+            print("   tiles in [%5d,%6s) launches %5d  ms %9.2f  flop %.3g  -> %.2f TFLOP/s   (mean K %.0f, mean tasks %.1f)" % (
+                lo, "inf" if hi > 1 << 29 else str(hi), msk.sum(), rows[msk, 0].sum(), rows[msk, 1].sum(),
+                rows[msk, 1].sum() / max(rows[msk, 0].sum(), 1e-9) / 1e9, rows[msk, 7].mean(), rows[msk, 3].mean()))
     other = [(kinds[L["kind"]], ms[i]) for i, L in enumerate(P.launches) if L["kind"] != 0]
     agg = {}
     for k, v in other:
