@@ -74,13 +74,13 @@ __device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double
 constexpr int GEMM_BK = 16;
 constexpr int GEMM_STAGES = 3;
 
-template <int BM, int BN>
+template <int BM, int BN, int BKT = GEMM_BK, int STG = GEMM_STAGES>
 constexpr int gemm_smem_bytes()
 {
     // worst case of the two layouts per operand
-    constexpr int a = (BM + 4) * GEMM_BK > BM * (GEMM_BK + 4) ? (BM + 4) * GEMM_BK : BM * (GEMM_BK + 4);
-    constexpr int b = (BN + 4) * GEMM_BK > BN * (GEMM_BK + 4) ? (BN + 4) * GEMM_BK : BN * (GEMM_BK + 4);
-    constexpr int pipe = GEMM_STAGES * (a + b) * 8;
+    constexpr int a = (BM + 4) * BKT > BM * (BKT + 4) ? (BM + 4) * BKT : BM * (BKT + 4);
+    constexpr int b = (BN + 4) * BKT > BN * (BKT + 4) ? (BN + 4) * BKT : BN * (BKT + 4);
+    constexpr int pipe = STG * (a + b) * 8;
     constexpr int epi = (BM + 2) * BN * 8;       // accumulator tile staged for the coalesced epilogue
     return pipe > epi ? pipe : epi;
 }
@@ -88,13 +88,13 @@ constexpr int gemm_smem_bytes()
 // Load one BT x BK operand tile into shared memory.
 //  KMAJ=false: element (i,kk) at g[i + col(kk)*ld]   -> smem[kk][BT+4]
 //  KMAJ=true : element (i,kk) at g[kk + i*ld]        -> smem[i][BK+4]
-template <int BT, bool KMAJ, int NT>
+template <int BT, bool KMAJ, int NT, int BKT>
 __device__ __forceinline__ void load_tile(double *smem, const double *g, int ld, int rows, int k0, int K,
                                           const int *gather, int tid)
 {
     if (!KMAJ) {
         constexpr int CH = BT / 2;               // 16-byte chunks per k-column
-        for (int id = tid; id < CH * GEMM_BK; id += NT) {
+        for (int id = tid; id < CH * BKT; id += NT) {
             const int kk = id / CH, ic = (id % CH) * 2;
             const int kg = k0 + kk;
             int bytes = 0;
@@ -107,7 +107,7 @@ __device__ __forceinline__ void load_tile(double *smem, const double *g, int ld,
             cp_async16(smem + kk * (BT + 4) + ic, src, bytes);
         }
     } else {
-        constexpr int CH = GEMM_BK / 2;          // 16-byte chunks per row
+        constexpr int CH = BKT / 2;          // 16-byte chunks per row
         for (int id = tid; id < CH * BT; id += NT) {
             const int i = id / CH, kc = (id % CH) * 2;
             const int kg = k0 + kc;
@@ -117,23 +117,23 @@ __device__ __forceinline__ void load_tile(double *smem, const double *g, int ld,
                 src = g + kg + (long long)i * ld;
                 bytes = (K - kg >= 2) ? 16 : 8;
             }
-            cp_async16(smem + i * (GEMM_BK + 4) + kc, src, bytes);
+            cp_async16(smem + i * (BKT + 4) + kc, src, bytes);
         }
     }
 }
 
-template <int BM, int BN, int WARPS_M, int WARPS_N, bool A_KMAJ, bool B_KMAJ>
+template <int BM, int BN, int WARPS_M, int WARPS_N, bool A_KMAJ, bool B_KMAJ, int BKT = GEMM_BK, int STG = GEMM_STAGES>
 __global__ void __launch_bounds__(WARPS_M *WARPS_N * 32)
 k_gemm_grouped(const GemmTask *__restrict__ tasks, const TileRef *__restrict__ tiles, GemmSpaces sp)
 {
     constexpr int NT = WARPS_M * WARPS_N * 32;
     constexpr int WM = BM / WARPS_M, WN = BN / WARPS_N;
     constexpr int MT = WM / 8, NTL = WN / 8;
-    constexpr int A_ELEMS = A_KMAJ ? BM * (GEMM_BK + 4) : (BM + 4) * GEMM_BK;
-    constexpr int B_ELEMS = B_KMAJ ? BN * (GEMM_BK + 4) : (BN + 4) * GEMM_BK;
+    constexpr int A_ELEMS = A_KMAJ ? BM * (BKT + 4) : (BM + 4) * BKT;
+    constexpr int B_ELEMS = B_KMAJ ? BN * (BKT + 4) : (BN + 4) * BKT;
     extern __shared__ __align__(16) double smem[];
     double *sA = smem;
-    double *sB = smem + GEMM_STAGES * A_ELEMS;
+    double *sB = smem + STG * A_ELEMS;
 
     pdl_enter();
     const TileRef tr = tiles[blockIdx.x];
@@ -153,42 +153,42 @@ k_gemm_grouped(const GemmTask *__restrict__ tasks, const TileRef *__restrict__ t
 #pragma unroll
         for (int b = 0; b < NTL; b++) { acc[a][b][0] = 0.0; acc[a][b][1] = 0.0; }
 
-    const int nk = (tk.K + GEMM_BK - 1) / GEMM_BK;
+    const int nk = (tk.K + BKT - 1) / BKT;
 #pragma unroll
-    for (int s = 0; s < GEMM_STAGES - 1; s++) {
+    for (int s = 0; s < STG - 1; s++) {
         if (s < nk) {
-            load_tile<BM, A_KMAJ, NT>(sA + s * A_ELEMS, gA, tk.lda, rowsA, s * GEMM_BK, tk.K, gather, tid);
-            load_tile<BN, B_KMAJ, NT>(sB + s * B_ELEMS, gB, tk.ldb, rowsB, s * GEMM_BK, tk.K, nullptr, tid);
+            load_tile<BM, A_KMAJ, NT, BKT>(sA + s * A_ELEMS, gA, tk.lda, rowsA, s * BKT, tk.K, gather, tid);
+            load_tile<BN, B_KMAJ, NT, BKT>(sB + s * B_ELEMS, gB, tk.ldb, rowsB, s * BKT, tk.K, nullptr, tid);
         }
         cp_async_commit();
     }
     const int lr = lane >> 2, lc = lane & 3;
     for (int kt = 0; kt < nk; kt++) {
-        cp_async_wait<GEMM_STAGES - 2>();
+        cp_async_wait<STG - 2>();
         __syncthreads();
         {   // prefetch stage kt + STAGES-1 into the slot freed by iteration kt-1
-            const int nx = kt + GEMM_STAGES - 1;
+            const int nx = kt + STG - 1;
             if (nx < nk) {
-                const int s = nx % GEMM_STAGES;
-                load_tile<BM, A_KMAJ, NT>(sA + s * A_ELEMS, gA, tk.lda, rowsA, nx * GEMM_BK, tk.K, gather, tid);
-                load_tile<BN, B_KMAJ, NT>(sB + s * B_ELEMS, gB, tk.ldb, rowsB, nx * GEMM_BK, tk.K, nullptr, tid);
+                const int s = nx % STG;
+                load_tile<BM, A_KMAJ, NT, BKT>(sA + s * A_ELEMS, gA, tk.lda, rowsA, nx * BKT, tk.K, gather, tid);
+                load_tile<BN, B_KMAJ, NT, BKT>(sB + s * B_ELEMS, gB, tk.ldb, rowsB, nx * BKT, tk.K, nullptr, tid);
             }
             cp_async_commit();
         }
-        const double *cA = sA + (kt % GEMM_STAGES) * A_ELEMS;
-        const double *cB = sB + (kt % GEMM_STAGES) * B_ELEMS;
+        const double *cA = sA + (kt % STG) * A_ELEMS;
+        const double *cB = sB + (kt % STG) * B_ELEMS;
 #pragma unroll
-        for (int k4 = 0; k4 < GEMM_BK; k4 += 4) {
+        for (int k4 = 0; k4 < BKT; k4 += 4) {
             double fa[MT], fb[NTL];
 #pragma unroll
             for (int a = 0; a < MT; a++) {
                 const int i = wm * WM + a * 8 + lr;
-                fa[a] = A_KMAJ ? cA[i * (GEMM_BK + 4) + k4 + lc] : cA[(k4 + lc) * (BM + 4) + i];
+                fa[a] = A_KMAJ ? cA[i * (BKT + 4) + k4 + lc] : cA[(k4 + lc) * (BM + 4) + i];
             }
 #pragma unroll
             for (int b = 0; b < NTL; b++) {
                 const int j = wn * WN + b * 8 + lr;
-                fb[b] = B_KMAJ ? cB[j * (GEMM_BK + 4) + k4 + lc] : cB[(k4 + lc) * (BN + 4) + j];
+                fb[b] = B_KMAJ ? cB[j * (BKT + 4) + k4 + lc] : cB[(k4 + lc) * (BN + 4) + j];
             }
 #pragma unroll
             for (int a = 0; a < MT; a++)

@@ -290,11 +290,22 @@ __global__ void __launch_bounds__(256) k_wtw(const WtwTask *__restrict__ tasks, 
     for (int e = threadIdx.x; e < NB * NB; e += 256) w[e % NB][e / NB] = dinv[t.w + e];
     __syncthreads();
     double *dst = sp.base[t.space] + t.dst;
-    for (int e = threadIdx.x; e < t.b * t.b; e += 256) {
-        const int i = e % t.b, j = e / t.b;
-        double s = 0.0;
-        for (int k = max(i, j); k < t.b; k++) s += w[k][i] * w[k][j];
-        dst[i + (long long)j * t.ldd] = s;
+    // thread = (row i, group of 16 columns): 16 independent accumulators, so the FP64 pipe latency (~40 cycles per
+    // dependent FMA) is hidden instead of serialised along each dot product.  W is lower triangular with explicit
+    // zeros above the diagonal, so k starts at i.
+    const int i = threadIdx.x & 63, jg = (threadIdx.x >> 6) * 16;
+    double acc[16];
+#pragma unroll
+    for (int u = 0; u < 16; u++) acc[u] = 0.0;
+    if (i < t.b && jg < t.b) {
+        for (int k = i; k < t.b; k++) {
+            const double wi = w[k][i];
+#pragma unroll
+            for (int u = 0; u < 16; u++) acc[u] += wi * w[k][jg + u];
+        }
+#pragma unroll
+        for (int u = 0; u < 16; u++)
+            if (jg + u < t.b) dst[i + (long long)(jg + u) * t.ldd] = acc[u];
     }
 }
 __global__ void k_extract(const ZEntry *__restrict__ ent, long long a0, long long a1, const double *__restrict__ zar,
@@ -334,11 +345,11 @@ static cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, siz
     return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
 }
 
-template <int BM, int BN, int WMn, int WNn, bool AK, bool BK_>
+template <int BM, int BN, int WMn, int WNn, bool AK, bool BK_, int BKT = GEMM_BK, int STG = GEMM_STAGES>
 static cudaError_t launch_gemm_variant(const Launch &L, const Program &P, const GemmSpaces &sp, cudaStream_t st)
 {
-    auto kern = k_gemm_grouped<BM, BN, WMn, WNn, AK, BK_>;
-    constexpr int smem = gemm_smem_bytes<BM, BN>();
+    auto kern = k_gemm_grouped<BM, BN, WMn, WNn, AK, BK_, BKT, STG>;
+    constexpr int smem = gemm_smem_bytes<BM, BN, BKT, STG>();
     static bool attr_done = false;
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -355,7 +366,7 @@ static cudaError_t launch_gemm(const Launch &L, const Program &P, const GemmSpac
     if (cfg == c && ak == A && bk == B) {                                                              \
         if (c == 0) return launch_gemm_variant<128, 128, 2, 4, A, B>(L, P, sp, st);                     \
         if (c == 1) return launch_gemm_variant<128, 64, 4, 2, A, B>(L, P, sp, st);                      \
-        return launch_gemm_variant<64, 64, 2, 2, A, B>(L, P, sp, st);                                   \
+        return launch_gemm_variant<64, 64, 2, 2, A, B, 32, 2>(L, P, sp, st);   /* k-tile 32, 2 stages */  \
     }
     V(0, false, false) V(0, false, true) V(0, true, false) V(0, true, true)
     V(1, false, false) V(1, false, true) V(1, true, false) V(1, true, true)
@@ -369,6 +380,13 @@ static cudaError_t launch_gemm(const Launch &L, const Program &P, const GemmSpac
         if (cfg == 6) return launch_gemm_variant<128, 128, 4, 2, false, false>(L, P, sp, st);   // 8 warps, 32x64
         if (cfg == 7) return launch_gemm_variant<256, 64, 8, 2, false, false>(L, P, sp, st);    // 16 warps, 32x32
         if (cfg == 8) return launch_gemm_variant<128, 64, 2, 4, false, false>(L, P, sp, st);    // 8 warps, 64x16
+        if (cfg == 9) return launch_gemm_variant<64, 64, 2, 2, false, false, 32, 2>(L, P, sp, st);    // k-tile 32, 2 stages
+        if (cfg == 10) return launch_gemm_variant<64, 64, 2, 2, false, false, 32, 3>(L, P, sp, st);   // k-tile 32, 3 stages
+        if (cfg == 11) return launch_gemm_variant<64, 64, 2, 2, false, false, 16, 4>(L, P, sp, st);   // 4 stages
+        if (cfg == 12) return launch_gemm_variant<64, 128, 2, 4, false, false, 32, 2>(L, P, sp, st);  // 64x128, k-tile 32
+        if (cfg == 13) return launch_gemm_variant<64, 64, 2, 2, false, false, 8, 4>(L, P, sp, st);    // k-tile 8, 4 stages
+        if (cfg == 14) return launch_gemm_variant<64, 64, 1, 4, false, false, 16, 3>(L, P, sp, st);   // warp tiles 64x16
+        if (cfg == 15) return launch_gemm_variant<64, 64, 4, 1, false, false, 16, 3>(L, P, sp, st);   // warp tiles 16x64
     }
     return cudaErrorInvalidValue;
 }
@@ -495,8 +513,9 @@ static void init_gemm_attributes()
     cudaFuncSetAttribute(k_gemm_grouped<BM, BN, WM, WN, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes<BM, BN>());  \
     cudaFuncSetAttribute(k_gemm_grouped<BM, BN, WM, WN, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes<BM, BN>());  \
     cudaFuncSetAttribute(k_gemm_grouped<BM, BN, WM, WN, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes<BM, BN>());
-    A(128, 128, 2, 4) A(128, 64, 4, 2) A(64, 64, 2, 2)
+    A(128, 128, 2, 4) A(128, 64, 4, 2)
 #undef A
+    // (the 64x64 production tile sets its attribute at first launch, launch_gemm_variant)
 }
 
 // Run a schedule: first call plainly, second call captured into a CUDA graph, later calls replayed.  The
@@ -898,9 +917,10 @@ extern "C" int spde_gemm_single(int cfg, int a_kmaj, int b_kmaj, int flags, int 
                                 const double *d_A, int lda, const double *d_B, int ldb, double *d_C, int ldc,
                                 int reps, float *h_ms, void *stream)
 {
-    if (cfg < 0 || cfg > 8 || M < 1 || N < 1 || K < 1) { set_error("spde_gemm_single: bad arguments"); return SPDE_ERR_ARG; }
+    if (cfg < 0 || cfg > 15 || M < 1 || N < 1 || K < 1) { set_error("spde_gemm_single: bad arguments"); return SPDE_ERR_ARG; }
     cudaStream_t st = (cudaStream_t)stream;
-    static const int BMs[9] = {128, 128, 64, 128, 128, 64, 128, 256, 128}, BNs[9] = {128, 64, 64, 64, 128, 128, 128, 64, 64};
+    static const int BMs[16] = {128, 128, 64, 128, 128, 64, 128, 256, 128, 64, 64, 64, 64, 64, 64, 64};
+    static const int BNs[16] = {128, 64, 64, 64, 128, 128, 128, 64, 64, 64, 64, 64, 128, 64, 64, 64};
     Program P;
     GemmTask t;
     memset(&t, 0, sizeof t);
