@@ -49,18 +49,26 @@ __global__ void k_extend_add(const ExtTask *__restrict__ tasks, const TileRef *_
     const int i = tr.ti * 32 + threadIdx.x;
     if (i >= t.nr) return;
     const int ri = rel[i];
-    for (int jj = threadIdx.y; jj < 32; jj += blockDim.y) {
-        const int j = tr.tj * 32 + jj;
-        if (j >= t.nr || j > i) continue;
-        const double v = src[i + (long long)j * t.lds];
-        const int rj = rel[j];
-        if (rj < t.pnc) {
-            const int row = ri < t.pnc ? ri : t.pncp + (ri - t.pnc);
-            panel[row + (long long)rj * t.pld] += v;
-        } else {
-            dst[t.pupd + (ri - t.pnc) + (long long)(rj - t.pnc) * t.pldu] += v;
+    const int prow = ri < t.pnc ? ri : t.pncp + (ri - t.pnc);
+    // the four columns of this thread are handled together: all index / source / destination loads are issued
+    // before the first dependent use, so each thread keeps 12 memory operations in flight (HBM-bound kernel)
+    double v[4], old[4];
+    double *q[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+        const int j = tr.tj * 32 + threadIdx.y + 8 * u;
+        q[u] = nullptr;
+        if (j < t.nr && j <= i) {
+            const int rj = rel[j];
+            v[u] = src[i + (long long)j * t.lds];
+            q[u] = rj < t.pnc ? panel + prow + (long long)rj * t.pld
+                              : dst + t.pupd + (ri - t.pnc) + (long long)(rj - t.pnc) * t.pldu;
         }
     }
+#pragma unroll
+    for (int u = 0; u < 4; u++) if (q[u]) old[u] = *q[u];
+#pragma unroll
+    for (int u = 0; u < 4; u++) if (q[u]) *q[u] = old[u] + v[u];
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -274,12 +282,20 @@ __global__ void k_selinv_gather(const GatherTask *__restrict__ tasks, const Tile
     if (i >= t.nr) return;
     int ri = rel[i];
     ri = ri < t.pnc ? ri : t.pncp + (ri - t.pnc);
-    for (int jj = threadIdx.y; jj < 32; jj += blockDim.y) {
-        const int j = tr.tj * 32 + jj;
-        if (j >= t.nr) continue;
-        int rj = rel[j];
-        rj = rj < t.pnc ? rj : t.pncp + (rj - t.pnc);
-        dst[(t.ncp + i) + (long long)(t.ncp + j) * t.ldd] = src[ri + (long long)rj * t.lds];
+    double v[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {       // four independent gathers in flight per thread
+        const int j = tr.tj * 32 + threadIdx.y + 8 * u;
+        if (j < t.nr) {
+            int rj = rel[j];
+            rj = rj < t.pnc ? rj : t.pncp + (rj - t.pnc);
+            v[u] = src[ri + (long long)rj * t.lds];
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+        const int j = tr.tj * 32 + threadIdx.y + 8 * u;
+        if (j < t.nr) dst[(t.ncp + i) + (long long)(t.ncp + j) * t.ldd] = v[u];
     }
 }
 __global__ void __launch_bounds__(256) k_wtw(const WtwTask *__restrict__ tasks, const double *__restrict__ dinv, GemmSpaces sp)

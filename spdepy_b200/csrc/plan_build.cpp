@@ -517,6 +517,8 @@ void Plan::build_selinv_program()
     const Symbolic &S = sym;
     const char *env = getenv("SPDE_SPLITK_MIN");          // test hook: exercise the split-K path on small meshes
     const int splitk_min = env ? std::max(8, atoi(env)) : 2048;
+    const char *envk = getenv("SPDE_SELINV_KCHUNK");
+    const int kchunk = envk ? atoi(envk) : 1024;    // measured on C3 (tools/kchunk_sweep.sh): none 786 ms, 1024 781, 512 792, 256 830
     for (int d = 0; d <= S.maxdepth; d++) {
         const std::vector<int> &lev = by_depth[d];
         const int sp_z = SP_Z0 + (d & 1), sp_par = SP_Z0 + ((d + 1) & 1);
@@ -578,11 +580,15 @@ void Plan::build_selinv_program()
                 // Z[below,p] = -Z[below,below] * Y   (and its transpose into the row block)
                 // Skinny product (N <= 64): for the big fronts near the root there are fewer row tiles than
                 // SMs, so K is split into chunks that accumulate atomically into the (still zero) block.
+                // The K chunks also bound the duration of one tile: a launch ends with a partially filled wave of
+                // CTAs, and with K = mb in the thousands one 64x64 tile runs for hundreds of microseconds
+                // (profiles/: mean selinv launch ~0.5 ms), so short chunks keep the tail of every launch short.
                 int nchunk = 1;
                 if (mb >= splitk_min) {
                     const int rowtiles = (mb + 127) / 128;
                     nchunk = std::max(1, std::min((2 * kSMs + rowtiles - 1) / rowtiles, mb / (splitk_min / 4)));
                 }
+                if (kchunk > 0 && mb > kchunk + kchunk / 2) nchunk = std::max(nchunk, (mb + kchunk - 1) / kchunk);
                 int clen = (mb + nchunk - 1) / nchunk;
                 clen += clen & 1;
                 for (int k0 = 0, ci = 0; k0 < mb; k0 += clen, ci++) {

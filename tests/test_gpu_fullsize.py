@@ -93,3 +93,45 @@ def test_hutchinson_scatters_around_exact(c2):
     est = np.array(est)
     sd = est.std(axis=0, ddof=1) / np.sqrt(est.shape[0]) + 1e-12
     assert np.all(np.abs(est.mean(axis=0) - jac) < 6 * sd + 1e-8), (est.mean(axis=0), jac, sd)
+
+
+def test_collapsed_prior_equals_3d_factorisation(c2):
+    """The time-collapsed prior (two 2-D factorisations, base.py:_prior_collapsed) against the 3-D factorisation of
+    the prior that the reference performs: log-determinant, likelihood and every gradient component."""
+    inp, mod = c2
+    m = mod.mod
+    par = inp["theta"]
+    m.collapse_prior = True
+    like_c, jac_c = m.logLike(par, grad=True, exact_grad=True)
+    ld_c = m.last["logdetQ"]
+    m.collapse_prior = False
+    try:
+        like_f, jac_f = m.logLike(par, grad=True, exact_grad=True)
+        ld_f = m.last["logdetQ"]
+    finally:
+        m.collapse_prior = True
+    assert abs(ld_c - ld_f) <= 1e-11 * abs(ld_f), (ld_c, ld_f)
+    assert abs(like_c - like_f) <= 1e-9 * abs(like_f)
+    assert np.abs(jac_c - jac_f).max() <= 1e-9 * np.abs(jac_f).max(), (jac_c, jac_f)
+    assert m.logLike(par, grad=False) == pytest.approx(like_c, rel=1e-12)
+
+
+def test_takahashi_residual_identity(c2):
+    """Size-independent property of the selected inverse: sum(Z .* Q) over the pattern = tr(Q^-1 Q) = n, and
+    diag(Z) agrees with Q^-1 e_j for a handful of columns."""
+    inp, mod = c2
+    m = mod.mod
+    st = m._assemble(inp["theta"])
+    eng = m.engine
+    from spdepy_b200.engine import Engine
+    eng.factorize(0, st["Q"])
+    Z = eng.selinv(0)
+    assert abs(Engine.dot(Z, st["Q"]) - eng.n) <= 1e-9 * eng.n
+    nd = eng.nslots // 2
+    cols = [0, 17, eng.n // 2, eng.n - 1]
+    E = torch.zeros(eng.n, len(cols), dtype=torch.float64, device="cuda")
+    for k, j in enumerate(cols):
+        E[j, k] = 1.0
+    X = eng.solve(0, E)
+    for k, j in enumerate(cols):
+        assert abs(float(X[j, k]) - float(Z[nd * eng.n + j])) <= 1e-9 * abs(float(X[j, k]))

@@ -191,3 +191,50 @@ def test_bordered_model_with_regression_columns(name, two):
     x[perm] = np.linalg.solve(L.T, z)
     ref = S.toarray() @ (x + mod.mu[:, None])
     assert relerr(X, ref) < 1e-9
+
+
+EDGE_CASES = [
+    # spde, mod0 spde, ha, ani, bc, M, N, T, ext, r, repeated observations
+    ("advection-diffusion", "whittle-matern", False, True, 3, 5, 4, 2, None, 3, True),      # two time slices, ragged mesh
+    ("advection-diffusion", "whittle-matern", False, False, 1, 6, 7, 3, 2, 1, False),       # isotropic, Neumann, extension
+    ("var-advection-var-diffusion", "var-whittle-matern", False, True, 2, 7, 6, 3, None, 2, True),   # periodic
+    ("whittle-matern", None, True, True, 3, 9, 5, None, None, 4, True),                      # spatial, half-angle
+    ("advection-var-diffusion", "whittle-matern", True, True, 3, 6, 6, 4, 1, 1, False),
+]
+
+
+@pytest.mark.parametrize("case", EDGE_CASES, ids=lambda c: "%s-bc%d-%dx%dx%s" % (c[0], c[4], c[5], c[6], c[7]))
+def test_edge_meshes_against_oracle(case):
+    """Small, ragged and minimal meshes (T = 2, M != N, periodic wrap on the smallest legal size), replicated data
+    (r > 1), repeated observation indices (S^T S holds counts) and a single observation: likelihood, exact gradient,
+    Hutchinson gradient with injected probes and the conditional mean against the CPU oracle."""
+    import spdepy_b200 as sp
+    spde, spde0, ha, ani, bc, M, N, T, ext, r, rep = case
+    x, y = np.linspace(0.0, 3.0, M), np.linspace(0.0, 2.5, N)
+    t = None if T is None else np.linspace(0.0, 0.6, T)
+    d = {"x": x, "y": y, "t": t, "T": T, "ext": ext, "spde": spde, "mod0_spde": spde0, "ha": ha, "ani": ani, "bc": bc}
+    g, g0 = make_grids(d)
+    kw = {}
+    if g0 is not None:
+        m0 = sp.model(grid=g0, spde=spde0, ha=ha, anisotropic=ani, bc=bc)
+        d["mod0_par"] = m0.mod.getPars()
+        kw["mod0"] = m0
+    mod = sp.model(grid=g, spde=spde, ha=ha, anisotropic=ani, bc=bc, **kw)
+    m = mod.mod
+    rng = np.random.default_rng(3)
+    nall = M * N * (T or 1)
+    for idx in (np.sort(rng.choice(nall, nall // 2, replace=rep)), np.array([nall // 3])):
+        data = rng.normal(size=(idx.size, r))
+        par = m.initFit(data, idx=idx, fitQ0=False)
+        par = par + 0.05 * rng.normal(size=par.size)
+        orc = make_oracle(d)
+        orc.initFit(data, idx=idx)
+        like_o, jac_o = orc.logLike_exact(par)
+        like, jac = m.logLike(par, grad=True, exact_grad=True)
+        assert abs(like - like_o) <= 1e-9 * abs(like_o), (like, like_o)
+        assert np.abs(jac - jac_o).max() <= 1e-9 * np.abs(jac_o).max(), (jac, jac_o)
+        probes = 2.0 * rng.integers(0, 2, size=(g.n, 8)) - 1.0
+        like_h, jac_h = m.logLike(par, grad=True, probes=probes)
+        like_ho, jac_ho = orc.logLike(par, nh1=8, grad=True, probes=probes)
+        assert abs(like_h - like_ho) <= 1e-9 * abs(like_ho)
+        assert np.abs(jac_h - jac_ho).max() <= 1e-9 * np.abs(jac_ho).max(), (jac_h, jac_ho)
