@@ -447,6 +447,9 @@ Program &Plan::solve_program(int k, int dir)
     Program &P = solve[key];
     const Symbolic &S = sym;
     const int kp = up2(k);
+    const bool blocked = k > 4;          // tensor-core path (see add_solve)
+    const char *envo = getenv("SPDE_SOLVE_OUTER");     // test hook: exercise the outer-block path on small meshes
+    const int OUTER = envo ? std::max(1, atoi(envo)) : spde::OUTER;
     if (dir == 0) {
         for (int d = S.maxdepth; d >= 0; d--) {
             LevelBuilder B(P);
@@ -454,17 +457,32 @@ Program &Plan::solve_program(int k, int dir)
                 const SNode &x = sn[s];
                 std::vector<Step> q;
                 const int64_t xs = (int64_t)x.first * kp;
-                for (int p = 0; p < x.nblk; p++) {
-                    const int c0 = p * NB, b = std::min(NB, x.nc - c0);
-                    // y_p = x_p W_p^T (in place)
-                    B.add_solve(q, B.task(SP_X, xs + (int64_t)c0 * kp, kp, SP_DINV, x.dinv + (int64_t)p * NB * NB, NB,
-                                         SP_X, xs + (int64_t)c0 * kp, kp, k, b, b, GF_BETA0), false);
-                    // remaining pivot columns of this supernode
-                    const int rest = x.nc - c0 - b;
-                    if (rest > 0)
-                        B.add_solve(q, B.task(SP_X, xs + (int64_t)c0 * kp, kp,
-                                             SP_L, x.panel + (c0 + b) + (int64_t)c0 * x.ld, x.ld,
-                                             SP_X, xs + (int64_t)(c0 + b) * kp, kp, k, rest, b, GF_NEG), false);
+                // Many right-hand sides (tensor-core path): two-level blocking as in the factorisation -- inside an
+                // outer block of OUTER*64 pivot columns the update after each 64-block stays inside the outer block
+                // (N <= 448), and one K = 512 update per outer block reaches the remaining pivot columns.  A few
+                // right-hand sides (matrix-vector path): one update of all remaining columns per 64-block.
+                const int outer = blocked ? OUTER : x.nblk;
+                for (int P0 = 0; P0 < x.nblk; P0 += outer) {
+                    const int P1 = std::min(P0 + outer, x.nblk);
+                    const int cEnd = std::min(P1 * NB, x.nc);
+                    for (int p = P0; p < P1; p++) {
+                        const int c0 = p * NB, b = std::min(NB, x.nc - c0);
+                        // y_p = x_p W_p^T (in place)
+                        B.add_solve(q, B.task(SP_X, xs + (int64_t)c0 * kp, kp, SP_DINV, x.dinv + (int64_t)p * NB * NB, NB,
+                                             SP_X, xs + (int64_t)c0 * kp, kp, k, b, b, GF_BETA0), false);
+                        // remaining pivot columns of this outer block
+                        const int rest = cEnd - c0 - b;
+                        if (rest > 0)
+                            B.add_solve(q, B.task(SP_X, xs + (int64_t)c0 * kp, kp,
+                                                 SP_L, x.panel + (c0 + b) + (int64_t)c0 * x.ld, x.ld,
+                                                 SP_X, xs + (int64_t)(c0 + b) * kp, kp, k, rest, b, GF_NEG), false);
+                    }
+                    if (cEnd < x.nc) {
+                        const int cP = P0 * NB;
+                        B.add_solve(q, B.task(SP_X, xs + (int64_t)cP * kp, kp,
+                                             SP_L, x.panel + cEnd + (int64_t)cP * x.ld, x.ld,
+                                             SP_X, xs + (int64_t)cEnd * kp, kp, k, x.nc - cEnd, cEnd - cP, GF_NEG), false);
+                    }
                 }
                 if (x.nr > 0) {
                     GemmTask t = B.task(SP_X, xs, kp, SP_L, x.panel + x.ncp, x.ld, SP_X, 0, kp, k, x.nr, x.nc,
@@ -490,16 +508,29 @@ Program &Plan::solve_program(int k, int dir)
                     t.aidx = (int)x.rows;
                     B.add_solve(q, t, true);
                 }
-                for (int p = x.nblk - 1; p >= 0; p--) {
-                    const int c0 = p * NB, b = std::min(NB, x.nc - c0);
-                    const int later = x.nc - c0 - b;
-                    if (later > 0)   // x_p -= X[later pivot columns] * L[later, p]
-                        B.add_solve(q, B.task(SP_X, xs + (int64_t)(c0 + b) * kp, kp,
-                                             SP_L, x.panel + (c0 + b) + (int64_t)c0 * x.ld, x.ld,
-                                             SP_X, xs + (int64_t)c0 * kp, kp, k, b, later, GF_NEG), true);
-                    // x_p = y_p W_p (in place)
-                    B.add_solve(q, B.task(SP_X, xs + (int64_t)c0 * kp, kp, SP_DINV, x.dinv + (int64_t)p * NB * NB, NB,
-                                         SP_X, xs + (int64_t)c0 * kp, kp, k, b, b, GF_BETA0), true);
+                // Many right-hand sides: left-looking only inside an outer block (K <= 448), then one right-looking
+                // K = 512 update of ALL earlier pivot columns per outer block -- a long-K product on a 64-column block
+                // would have k/64 tiles for the whole machine (measured: 1024 samples on C3 at ~5 TFLOP/s).
+                const int outer = blocked ? OUTER : x.nblk;
+                const int nouter = (x.nblk + outer - 1) / outer;
+                for (int o = nouter - 1; o >= 0; o--) {
+                    const int P0 = o * outer, P1 = std::min(P0 + outer, x.nblk);
+                    const int cEnd = std::min(P1 * NB, x.nc), cP = P0 * NB;
+                    for (int p = P1 - 1; p >= P0; p--) {
+                        const int c0 = p * NB, b = std::min(NB, x.nc - c0);
+                        const int later = cEnd - c0 - b;
+                        if (later > 0)   // x_p -= X[later pivot columns of the outer block] * L[later, p]
+                            B.add_solve(q, B.task(SP_X, xs + (int64_t)(c0 + b) * kp, kp,
+                                                 SP_L, x.panel + (c0 + b) + (int64_t)c0 * x.ld, x.ld,
+                                                 SP_X, xs + (int64_t)c0 * kp, kp, k, b, later, GF_NEG), true);
+                        // x_p = y_p W_p (in place)
+                        B.add_solve(q, B.task(SP_X, xs + (int64_t)c0 * kp, kp, SP_DINV, x.dinv + (int64_t)p * NB * NB, NB,
+                                             SP_X, xs + (int64_t)c0 * kp, kp, k, b, b, GF_BETA0), true);
+                    }
+                    if (cP > 0)          // X[earlier pivot columns] -= X[outer block] * L[outer block, earlier]
+                        B.add_solve(q, B.task(SP_X, xs + (int64_t)cP * kp, kp,
+                                             SP_L, x.panel + cP, x.ld,
+                                             SP_X, xs, kp, k, cP, cEnd - cP, GF_NEG), true);
                 }
                 B.seq.push_back(std::move(q));
             }

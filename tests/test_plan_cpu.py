@@ -160,3 +160,38 @@ def test_emulated_selinv_split_k(monkeypatch):
     full = pat.to_csc(Zq).toarray()
     mask = pat.to_csc(np.ones(pat.nslots * n)).toarray() != 0
     assert np.abs(full[mask] - Zd[mask]).max() < 1e-10 * np.abs(Zd).max()
+
+
+@pytest.mark.parametrize("outer", ["1", "2"])
+def test_emulated_blocked_multi_rhs_solves(outer, monkeypatch):
+    """Solves with more than four right-hand sides use the two-level blocked schedule (outer blocks of pivot columns);
+    SPDE_SOLVE_OUTER shrinks the outer block so that small meshes exercise it."""
+    from spdepy_b200 import _lib
+    monkeypatch.setenv("SPDE_SOLVE_OUTER", outer)
+    M, N, T = 18, 16, 5
+    plan = _lib.PlanHandle(M, N, T, 3)
+    first, rowptr, rows, parent = plan.supernodes()
+    assert np.diff(first).max() > 64 * int(outer), "mesh too small to reach the outer-block path"
+    n = plan.n
+    from spdepy_b200.pattern import Pattern
+    pat = Pattern(M, N, T, 3)
+    rng = np.random.default_rng(1)
+    # a symmetric, strictly diagonally dominant matrix on the Q43 pattern
+    ones = pat.to_csc(np.ones(43 * n))
+    A = ones.multiply(1.0).tocsr()
+    A.data[:] = rng.uniform(-1.0, 1.0, size=A.data.size)
+    A = (A + A.T) * 0.5
+    A = A + sparse.diags(np.asarray(abs(A).sum(axis=1)).ravel() + 1.0)
+    flat = pat.from_sparse(A.tocsc())
+    em = pe.Emulator(plan)
+    assert em.factorize(flat, None, 0.0) == 0
+    Ad = A.toarray()
+    B = rng.normal(size=(n, 6))
+    X = em.solve(B, mode=15)
+    assert np.abs(X - np.linalg.solve(Ad, B)).max() < 1e-9 * np.abs(X).max()
+    perm = plan.perm.astype(np.int64)
+    Lref = np.linalg.cholesky(Ad[np.ix_(perm, perm)])
+    Zs = em.solve(B, mode=10)
+    ref = np.empty_like(B)
+    ref[perm] = np.linalg.solve(Lref.T, B)
+    assert np.abs(Zs - ref).max() < 1e-9 * np.abs(ref).max()
