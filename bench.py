@@ -347,12 +347,18 @@ def run_ours(args):
         alg_flops = (3.0 if collapsed else 6.0) * stats["flops"]
         peak = fp64_peak()
         achieved = alg_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None
+        traffic, traffic_note = None, "no ncu capture for this workload"
+        tpath = os.path.join(ROOT, "profiles", "r1_gemm_traffic_%s.json" % ("c3" if name == "c5" else name))
+        if os.path.exists(tpath):
+            tj = json.load(open(tpath))
+            traffic = tj["traffic_bytes_per_launch"]
+            traffic_note = ("dram__bytes_read.sum + dram__bytes_write.sum summed over the %d k_gemm_grouped launches of one "
+                            "evaluation (%.0f GB read, %.0f GB written) / launches, from %s; the largest launch alone: DMMA pipe "
+                            "83%% active, L2 hit 77%% (profiles/r1_ncu_gemm_full_summary.json)"
+                            % (tj["launches"], tj["dram_read_bytes"] / 1e9, tj["dram_write_bytes"] / 1e9, os.path.basename(tpath)))
         roof = {"bound": "tensor", "kernel": "k_gemm_grouped (FP64 DMMA m8n8k4)", "achieved": achieved, "peak": peak,
-                "unit": "TFLOP/s", "frac": (achieved / peak) if achieved else None, "traffic": None,
-                "traffic_note": "ncu --set full of the largest grouped launch of this workload (19718 CTAs, 25.4 ms): "
-                                "dram read 16.46 GB + write 1.58 GB, DMMA pipe 83% active, L2 hit 77% "
-                                "(profiles/r1_ncu_gemm_full_summary.json); a per-launch average over the ~4400 launches "
-                                "of a step is not captured",
+                "unit": "TFLOP/s", "frac": (achieved / peak) if achieved else None, "traffic": traffic,
+                "traffic_note": traffic_note,
                 "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (MEASURED_PEAKS.json has no FP64 figure)",
                 "launches_per_step": gemm_launches, "avg_launch_ms": gemm_ms / max(gemm_launches, 1),
                 "gemm_share_of_scheduled_time": gemm_ms / total_ms if total_ms else None,
