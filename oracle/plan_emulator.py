@@ -14,12 +14,12 @@ import numpy as np
 
 GF_LOWER, GF_BETA0, GF_NEG, GF_ATOMIC, GF_GATHER_A, GF_SCATTER_C, GF_MIRROR = (1 << 9, 1 << 10, 1 << 11, 1 << 12,
                                                                             1 << 13, 1 << 14, 1 << 15)
-LK_GEMM, LK_POTRF, LK_EXTADD, LK_ZERO, LK_GATHER, LK_WTW, LK_EXTRACT, LK_GEMV = range(8)
+LK_GEMM, LK_POTRF, LK_EXTADD, LK_ZERO, LK_GATHER, LK_WTW, LK_EXTRACT, LK_GEMV, LK_SYNC = range(9)
 NB = 64
 CFG = {0: (128, 128), 1: (128, 64), 2: (64, 64)}
 
 LAUNCH = np.dtype([("kind", "i4"), ("variant", "i4"), ("task0", "i8"), ("ntasks", "i4"), ("tile0", "i8"),
-                   ("ntiles", "i4"), ("a0", "i8"), ("a1", "i8")], align=True)
+                   ("ntiles", "i4"), ("a0", "i8"), ("a1", "i8"), ("lane", "i4"), ("pad", "i4")], align=True)
 GEMM = np.dtype([("a", "i8"), ("b", "i8"), ("c", "i8"), ("c2", "i8"), ("lda", "i4"), ("ldb", "i4"), ("ldc", "i4"),
                  ("M", "i4"), ("N", "i4"), ("K", "i4"), ("flags", "i4"), ("aidx", "i4"), ("cidx", "i4"), ("pad", "i4")],
                 align=True)
@@ -213,6 +213,8 @@ class Emulator:
                 self._gather(P, L)
             elif kind == LK_WTW:
                 self._wtw(P, L)
+            elif kind == LK_SYNC:
+                continue        # lane ordering: the launch list is a valid serial order
             elif kind == LK_EXTRACT:
                 e = zent[int(L["a0"]):int(L["a1"])]
                 v = self.sp[int(L["variant"])][e["src"]]

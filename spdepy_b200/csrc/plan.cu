@@ -466,7 +466,38 @@ static int issue_program(Plan &p, Program &P, int which, cudaStream_t st, double
     const int pdl_saved = g_pdl;
     if (p.prof_on) g_pdl = 0;          // per-launch events need plain stream order
     struct Restore { int v; ~Restore() { g_pdl = v; } } restore{pdl_saved};
+    // two-lane schedules: the bulk lane gets its own stream, ordered against the main lane by LK_SYNC records
+    const bool lanes = p.use_lanes && !p.prof_on;
+    const cudaStream_t main_st = st;
+    cudaStream_t bulk_st = st;
+    if (lanes) {
+        if (!p.bulk_stream[which]) {
+            // lowest priority: CTAs of the main lane (the latency-bound panel chain) are dispatched first whenever
+            // an SM slot frees up, the bulk GEMMs fill what is left
+            int least = 0, greatest = 0;
+            SPDE_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+            SPDE_CUDA_CHECK(cudaStreamCreateWithPriority(&p.bulk_stream[which], cudaStreamNonBlocking, least));
+            SPDE_CUDA_CHECK(cudaEventCreateWithFlags(&p.bulk_fork[which], cudaEventDisableTiming));
+            for (int e = 0; e < 2; e++) SPDE_CUDA_CHECK(cudaEventCreateWithFlags(&p.bulk_ev[which][e], cudaEventDisableTiming));
+        }
+        bulk_st = p.bulk_stream[which];
+    }
     for (const Launch &L : P.launches) {
+        if (L.kind == LK_SYNC) {
+            if (lanes) {
+                if (L.variant == 0) {
+                    SPDE_CUDA_CHECK(cudaEventRecord(p.bulk_fork[which], main_st));
+                    SPDE_CUDA_CHECK(cudaStreamWaitEvent(bulk_st, p.bulk_fork[which], 0));
+                } else if (L.variant == 1) {
+                    SPDE_CUDA_CHECK(cudaEventRecord(p.bulk_ev[which][L.a0 & 1], bulk_st));
+                } else {
+                    SPDE_CUDA_CHECK(cudaStreamWaitEvent(main_st, p.bulk_ev[which][L.a0 & 1], 0));
+                }
+            }
+            if (p.prof_on) cudaEventRecord(ev[++li], st);
+            continue;
+        }
+        st = (lanes && L.lane == 1) ? bulk_st : main_st;
         switch (L.kind) {
         case LK_GEMM:
             SPDE_CUDA_CHECK(launch_gemm(L, P, sp, st));
@@ -502,6 +533,7 @@ static int issue_program(Plan &p, Program &P, int which, cudaStream_t st, double
         if (L.kind != LK_ZERO) count_launch();
         if (p.prof_on) cudaEventRecord(ev[++li], st);
     }
+    st = main_st;
     if (p.prof_on) {
         SPDE_CUDA_CHECK(cudaStreamSynchronize(st));
         P.last_ms.assign(P.launches.size(), 0.f);
@@ -510,6 +542,7 @@ static int issue_program(Plan &p, Program &P, int which, cudaStream_t st, double
             cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
             P.last_ms[i] = ms;
             const Launch &L = P.launches[i];
+            if (L.kind == LK_SYNC) continue;
             const int v = L.kind == LK_GEMM ? L.variant : 0;
             p.prof_ms[L.kind][v] += ms;
             p.prof_cnt[L.kind][v] += 1;
@@ -565,7 +598,9 @@ static int run_program(Plan &p, Program &P, int which, cudaStream_t st, double *
         P.graph[which] = nullptr;
     }
     if (!p.cap_stream[which]) {
-        SPDE_CUDA_CHECK(cudaStreamCreateWithFlags(&p.cap_stream[which], cudaStreamNonBlocking));
+        int least = 0, greatest = 0;
+        SPDE_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+        SPDE_CUDA_CHECK(cudaStreamCreateWithPriority(&p.cap_stream[which], cudaStreamNonBlocking, greatest));
         SPDE_CUDA_CHECK(cudaEventCreateWithFlags(&p.ev_in[which], cudaEventDisableTiming));
         SPDE_CUDA_CHECK(cudaEventCreateWithFlags(&p.ev_out[which], cudaEventDisableTiming));
     }
@@ -590,7 +625,7 @@ static int run_program(Plan &p, Program &P, int which, cudaStream_t st, double *
         P.graph_key[which] = key;
     }
     int nk = 0;
-    for (const Launch &L : P.launches) nk += L.kind != LK_ZERO;
+    for (const Launch &L : P.launches) nk += (L.kind != LK_ZERO && L.kind != LK_SYNC);
     count_launch(nk);
     if (lane == 1) {
         SPDE_CUDA_CHECK(cudaEventRecord(p.sev_in[which], st));
@@ -617,6 +652,8 @@ static int ensure_device(Plan &p, int which)
         if (env) p.use_graphs = atoi(env);
         const char *pdl = getenv("SPDE_PDL");
         if (pdl) g_pdl = atoi(pdl);
+        const char *ln = getenv("SPDE_LANES");
+        if (ln) p.use_lanes = atoi(ln);
     }
     if (!(p.device_ready & 1)) {
         std::vector<int> idx(p.sym.rows);
@@ -674,6 +711,10 @@ extern "C" void spde_plan_destroy(spde_plan *pp)
         cudaFree(p->d_L[a]); cudaFree(p->d_dinv[a]); cudaFree(p->d_ybuf[a]); cudaFree(p->d_zq[a]);
         for (int b = 0; b < 2; b++) { cudaFree(p->d_arena[a][b]); cudaFree(p->d_zarena[a][b]); }
         if (p->cap_stream[a]) { cudaStreamDestroy(p->cap_stream[a]); cudaEventDestroy(p->ev_in[a]); cudaEventDestroy(p->ev_out[a]); }
+        if (p->bulk_stream[a]) {
+            cudaStreamDestroy(p->bulk_stream[a]); cudaEventDestroy(p->bulk_fork[a]);
+            cudaEventDestroy(p->bulk_ev[a][0]); cudaEventDestroy(p->bulk_ev[a][1]);
+        }
         if (p->solve_stream[a]) { cudaStreamDestroy(p->solve_stream[a]); cudaEventDestroy(p->sev_in[a]); cudaEventDestroy(p->sev_out[a]); }
     }
     cudaFree(p->d_X); cudaFree(p->d_red); cudaFree(p->d_idx); cudaFree(p->d_qdest);

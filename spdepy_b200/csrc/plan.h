@@ -39,13 +39,17 @@ struct GatherTask {   // selected inverse: child's trailing block <- parent's fr
 };
 struct WtwTask { long long w; long long dst; int ldd, b, space, pad; };
 
-enum LaunchKind : int { LK_GEMM = 0, LK_POTRF, LK_EXTADD, LK_ZERO, LK_GATHER, LK_WTW, LK_EXTRACT, LK_GEMV };
+enum LaunchKind : int { LK_GEMM = 0, LK_POTRF, LK_EXTADD, LK_ZERO, LK_GATHER, LK_WTW, LK_EXTRACT, LK_GEMV, LK_SYNC };
+// LK_SYNC (two-lane schedules): variant 0 = the bulk lane waits for everything issued so far on the main lane,
+// 1 = record bulk-lane event a0, 2 = the main lane waits for bulk-lane event a0.  The launch list is always a valid
+// serial order, so an executor may ignore the lanes (profiling mode, the NumPy interpreter).
 
 struct Launch {
     int kind, variant;
     int64_t task0; int ntasks;
     int64_t tile0; int ntiles;
     int64_t a0, a1;   // LK_ZERO: [a0,a1) doubles of space `variant`; LK_EXTRACT: entry range
+    int lane, pad;    // 0 = main lane, 1 = bulk lane (trailing updates that overlap the next panel)
 };
 
 struct Program {
@@ -112,6 +116,9 @@ struct Plan {
     bool pending_readonly[2] = {false, false};   // ... and it only READS the factor (Takahashi): solves may run beside it
     // second lane for the triangular solves, so that the latency-bound k = 1 solve of the conditional mean overlaps
     // the Takahashi pass of the same store
+    cudaStream_t bulk_stream[2] = {nullptr, nullptr};        // second lane of the factor schedule (look-ahead)
+    cudaEvent_t bulk_fork[2] = {nullptr, nullptr}, bulk_ev[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+    int use_lanes = 1;
     cudaStream_t solve_stream[2] = {nullptr, nullptr};
     cudaEvent_t sev_in[2] = {nullptr, nullptr}, sev_out[2] = {nullptr, nullptr};
     double *d_zq[2] = {nullptr, nullptr};

@@ -348,6 +348,13 @@ void Plan::build_factor_program()
     std::vector<std::vector<int>> kids(S.nsuper);
     for (int s = 0; s < S.nsuper; s++)
         if (sn[s].parent >= 0) kids[sn[s].parent].push_back(s);
+    const char *envl = getenv("SPDE_LOOKAHEAD");
+    // Measured on B200 (tools/lookahead_ab.sh, C3): 792 ms per evaluation with the two-lane schedule vs 783 ms without,
+    // with or without stream priorities -- the small panel kernels then queue behind resident bulk-GEMM CTAs (no
+    // preemption, ~half a tile time per launch), which costs what the overlap gains.  Off by default.
+    const bool lookahead = envl ? atoi(envl) != 0 : false;
+    const char *envo = getenv("SPDE_FACTOR_OUTER");     // test hook: small outer blocks exercise the look-ahead on small meshes
+    const int OUTER = envo ? std::max(1, atoi(envo)) : spde::OUTER;
     for (int d = S.maxdepth; d >= 0; d--) {
         const std::vector<int> &lev = by_depth[d];
         const int sp_u = SP_AR0 + (d & 1), sp_child = SP_AR0 + ((d + 1) & 1);
@@ -386,6 +393,110 @@ void Plan::build_factor_program()
             if (L.ntiles) P.launches.push_back(L);
         }
         // dense partial Cholesky of every front of the level
+        int maxblk = 0;
+        for (int s : lev) maxblk = std::max(maxblk, sn[s].nblk);
+        if (lookahead && maxblk > OUTER) {
+            // Two-lane schedule with look-ahead (levels whose fronts span several outer blocks, i.e. the top of the
+            // tree): the panel of outer block O+1 -- a chain of small, latency-bound launches -- runs on the main lane
+            // while the far part of the trailing update of block O and the update-matrix contribution of block O run
+            // on the bulk lane.  Per outer block O:
+            //   main: [wait far(O-2)]  near(O-1): block O-1 -> the columns of block O;   panel(O)
+            //   bulk: [after panel(O)]  far(O): block O -> the columns beyond block O+1;  U -= L21[:,O] L21[:,O]^T
+            // near(O-1) and far(O-2) write the same columns, hence the wait; everything else is disjoint.
+            auto sync = [&](int variant, int ev) {
+                Launch L;
+                memset(&L, 0, sizeof L);
+                L.kind = LK_SYNC; L.variant = variant; L.a0 = ev;
+                P.launches.push_back(L);
+            };
+            const int maxO = (maxblk + OUTER - 1) / OUTER;
+            for (int O = 0; O < maxO; O++) {
+                const int P0 = O * OUTER;
+                if (O >= 1) {
+                    if (O >= 2) sync(2, (O - 2) & 1);
+                    LevelBuilder Bn(P);
+                    for (int s : lev) {
+                        const SNode &x = sn[s];
+                        if (x.nblk <= P0) continue;
+                        const int mrows = x.ncp + x.nr;
+                        const int cPp = (P0 - OUTER) * NB, cP = P0 * NB, cE = std::min((P0 + OUTER) * NB, x.nc);
+                        std::vector<Step> q;
+                        Bn.add_gemm(q, Bn.task(SP_L, x.panel + cP + (int64_t)cPp * x.ld, x.ld,
+                                               SP_L, x.panel + cP + (int64_t)cPp * x.ld, x.ld,
+                                               SP_L, x.panel + cP + (int64_t)cP * x.ld, x.ld,
+                                               mrows - cP, cE - cP, cP - cPp, GF_NEG | GF_LOWER), false, false);
+                        Bn.seq.push_back(std::move(q));
+                    }
+                    Bn.flush();
+                }
+                {
+                    LevelBuilder Bp(P);
+                    for (int s : lev) {
+                        const SNode &x = sn[s];
+                        if (x.nblk <= P0) continue;
+                        const int mrows = x.ncp + x.nr;
+                        const int P1 = std::min(P0 + OUTER, x.nblk), cP = P0 * NB;
+                        std::vector<Step> q;
+                        for (int p = P0; p < P1; p++) {
+                            const int c0 = p * NB, b = std::min(NB, x.nc - c0);
+                            if (p > P0)
+                                Bp.add_gemm(q, Bp.task(SP_L, x.panel + c0 + (int64_t)cP * x.ld, x.ld,
+                                                       SP_L, x.panel + c0 + (int64_t)cP * x.ld, x.ld,
+                                                       SP_L, x.panel + c0 + (int64_t)c0 * x.ld, x.ld,
+                                                       mrows - c0, b, c0 - cP, GF_NEG), false, false);
+                            Step st;
+                            memset(&st, 0, sizeof st);
+                            st.kind = LK_POTRF;
+                            st.p.blk = x.panel + c0 + (int64_t)c0 * x.ld;
+                            st.p.dinv = x.dinv + (int64_t)p * NB * NB;
+                            st.p.ld = x.ld; st.p.b = b; st.p.col0 = x.first + c0;
+                            q.push_back(st);
+                            const int r0 = (p == x.nblk - 1) ? x.ncp : c0 + NB;
+                            Bp.add_gemm(q, Bp.task(SP_L, x.panel + r0 + (int64_t)c0 * x.ld, x.ld,
+                                                   SP_DINV, st.p.dinv, NB,
+                                                   SP_L, x.panel + r0 + (int64_t)c0 * x.ld, x.ld,
+                                                   mrows - r0, b, b, GF_BETA0), false, false);
+                        }
+                        Bp.seq.push_back(std::move(q));
+                    }
+                    Bp.flush();
+                }
+                sync(0, 0);
+                const size_t from = P.launches.size();
+                {
+                    LevelBuilder Bf(P);
+                    for (int s : lev) {
+                        const SNode &x = sn[s];
+                        if (x.nblk <= P0) continue;
+                        const int mrows = x.ncp + x.nr;
+                        const int cP = P0 * NB, cE = std::min((P0 + OUTER) * NB, x.nc);
+                        const int c2 = std::min((P0 + 2 * OUTER) * NB, x.nc);      // end of the next outer block
+                        std::vector<Step> q;
+                        bool opened = false;
+                        if (c2 < x.nc) {
+                            Bf.add_gemm(q, Bf.task(SP_L, x.panel + c2 + (int64_t)cP * x.ld, x.ld,
+                                                   SP_L, x.panel + c2 + (int64_t)cP * x.ld, x.ld,
+                                                   SP_L, x.panel + c2 + (int64_t)c2 * x.ld, x.ld,
+                                                   mrows - c2, x.nc - c2, cE - cP, GF_NEG | GF_LOWER), false, false);
+                            opened = true;
+                        }
+                        if (x.nr > 0) {
+                            GemmTask u = Bf.task(SP_L, x.panel + x.ncp + (int64_t)cP * x.ld, x.ld,
+                                                 SP_L, x.panel + x.ncp + (int64_t)cP * x.ld, x.ld,
+                                                 sp_u, x.upd, x.ldu, x.nr, x.nr, cE - cP, GF_NEG | GF_LOWER);
+                            if (opened) Bf.join_gemm(q, u);
+                            else Bf.add_gemm(q, u, false, false);
+                        }
+                        if (!q.empty()) Bf.seq.push_back(std::move(q));
+                    }
+                    Bf.flush();
+                }
+                for (size_t i = from; i < P.launches.size(); i++) P.launches[i].lane = 1;
+                sync(1, O & 1);
+            }
+            sync(2, (maxO - 1) & 1);
+            continue;
+        }
         LevelBuilder B(P);
         for (int s : lev) {
             const SNode &x = sn[s];

@@ -168,6 +168,8 @@ def test_emulated_blocked_multi_rhs_solves(outer, monkeypatch):
     SPDE_SOLVE_OUTER shrinks the outer block so that small meshes exercise it."""
     from spdepy_b200 import _lib
     monkeypatch.setenv("SPDE_SOLVE_OUTER", outer)
+    monkeypatch.setenv("SPDE_FACTOR_OUTER", outer)      # also the two-lane look-ahead factor schedule (near / far / U pieces)
+    monkeypatch.setenv("SPDE_LOOKAHEAD", "1")
     M, N, T = 18, 16, 5
     plan = _lib.PlanHandle(M, N, T, 3)
     first, rowptr, rows, parent = plan.supernodes()
@@ -184,8 +186,14 @@ def test_emulated_blocked_multi_rhs_solves(outer, monkeypatch):
     A = A + sparse.diags(np.asarray(abs(A).sum(axis=1)).ravel() + 1.0)
     flat = pat.from_sparse(A.tocsc())
     em = pe.Emulator(plan)
+    launches = pe.Program(plan, 0).launches
+    assert (launches["kind"] == pe.LK_SYNC).sum() > 0
+    if outer == "1":
+        assert (launches["lane"] == 1).sum() > 0
     assert em.factorize(flat, None, 0.0) == 0
     Ad = A.toarray()
+    sign, ld = np.linalg.slogdet(Ad)
+    assert abs(em.logdet() - ld) < 1e-10 * abs(ld)
     B = rng.normal(size=(n, 6))
     X = em.solve(B, mode=15)
     assert np.abs(X - np.linalg.solve(Ad, B)).max() < 1e-9 * np.abs(X).max()
