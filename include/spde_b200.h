@@ -90,6 +90,17 @@ int spde_fill_spacetime(int M, int N, int T, int bc, const double *d_AtDA25, con
                         const double *d_kappa, int kvar, double V, const double *d_Q0_25,
                         double sigma, double dt, int divide, double *d_Q43, void *stream);
 
+/* Separable space-time precision Q = Qt (x) Qs (seperable_spatial_temporal2D.py:82) into the Q75 layout: slot =
+ * (dt+1)*25 + (dj+2)*5 + (di+2), address q[slot*n + t*Ns + cell].  Qt = tridiag with diagonal (d0, d1, ..., d1, d0) and
+ * off-diagonal e (makeQt, :186-211).  Every function that takes `bc` selects this 75-slot pattern when
+ * SPDE_PATTERN_KRON is or-ed into it (spde_plan_create, spde_q_apply, spde_sddmm); T >= 2. */
+#define SPDE_PATTERN_KRON (1 << 8)
+int spde_fill_kron(int M, int N, int T, int bc, const double *d_Qs25, double d0, double d1, double e,
+                   double *d_Q75, void *stream);
+/* Adjoint of spde_fill_kron with respect to Qs: Wd25[q][cell] = sum_t sum_dt Qt[t,t+dt] * W75[(dt+1)*25+q][(cell,t)]. */
+int spde_kron_reduce(int M, int N, int T, int bc, const double *d_W75, double d0, double d1, double e,
+                     double *d_Wd25, void *stream);
+
 /* ------------------------------------------------------------------ symbolic plan (host, once per mesh) */
 
 /* Geometric nested dissection + elimination tree + supernodes + level schedule + kernel task

@@ -46,6 +46,9 @@ CASES = [
     ("cad_ani_bc1_q0", "cov-advection-diffusion", False, True, 1, (8, 7, 3), None, "whittle-matern", True),
     ("cavd_ha_bc3", "cov-advection-var-diffusion", True, True, 3, (8, 7, 3), None, "whittle-matern", False),
     ("vavd_iso_bc3_q0", "var-advection-var-diffusion", False, False, 3, (8, 7, 3), None, "whittle-matern", True),
+    # separable space-time model Q = Qt (x) Qs (the reference ignores mod0 for this family)
+    ("sep_ani_bc3", "seperable-spatial-temporal", False, True, 3, (8, 7, 4), None, "whittle-matern", False),
+    ("sep_ani_bc1_ext", "seperable-spatial-temporal", False, True, 1, (7, 6, 3), 1, "whittle-matern", False),
 ]
 
 
@@ -114,7 +117,8 @@ def run_case(case):
     # intermediate quantities (recomputed exactly as logLike does, advection_diffusion2D.py:190-198)
     from sksparse.cholmod import cholesky
     tau = np.exp(par[-1])
-    Qm, Qf, _ = mod.mod.makeQ(par=par, grad=False)
+    res = mod.mod.makeQ(par=par, grad=False)          # (Q, Q_fac, None) or, for the separable class, (Q, Q_fac)
+    Qm, Qf = res[0], res[1]
     S = mod.mod.S
     Qc = Qm + S.T @ S * tau
     Qcf = cholesky(Qc)

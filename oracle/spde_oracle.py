@@ -493,6 +493,57 @@ class OracleSPDE:
         return -like / (nobs * self.r), -g_par / (nobs * self.r)
 
 
+class OracleSeparable(OracleSPDE):
+    """Restatement of ``SeperableSpatialTemporal2D`` (``seperable_spatial_temporal2D.py:64-122, 186-211``):
+    ``Q = kron(Qt, Qs)``, ``Qs`` the spatially varying anisotropic Whittle-Matern precision, ``Qt`` AR(1).
+    ``par = [kappa x9, gamma x9, vx x9, vy x9, log rho, log tau]``; ``logLike`` / ``logLike_exact`` are inherited (the
+    reference's ``logLike`` body is the common one, ``:125-170``)."""
+
+    def __init__(self, grid, par=None, bc: int = 3):
+        super().__init__("var-whittle-matern-anisotropic-2D", grid, None, None, bc)
+        self.type = "seperable-spatial-temporal-ani-2D-bc%d" % bc
+        if par is not None:
+            self.setQ(par)
+
+    @staticmethod
+    def makeQt(rho, T, diff=0):
+        res = np.zeros((T, T))
+        for i in range(T):
+            if diff == 1:
+                res[i, i] = (2 if i == 0 or i == T - 1 else 4) * rho ** 2 / (1 - rho ** 2) ** 2
+                off = -rho * (1 + rho ** 2) / (1 - rho ** 2) ** 2
+            else:
+                res[i, i] = 1 / (1 - rho ** 2) if i == 0 or i == T - 1 else (1 + rho ** 2) / (1 - rho ** 2)
+                off = -rho / (1 - rho ** 2)
+            if i > 0:
+                res[i, i - 1] = off
+            if i < T - 1:
+                res[i, i + 1] = off
+        return sparse.csc_matrix(res)
+
+    def makeQ(self, par, grad=True):
+        par = np.asarray(par, dtype="float64")
+        T = self.grid.T
+        Qs, _, dQs = self._makeQ_spatial(np.hstack([par[:36], par[-1]]), grad)
+        rho = np.exp(par[36])
+        Qt = self.makeQt(rho, T)
+        Q = sparse.kron(Qt, Qs).tocsc()
+        Q_fac = cholesky(Q)
+        if not grad:
+            return Q, Q_fac, None
+        dQ = [sparse.kron(Qt, d).tocsc() for d in dQs]
+        dQ.append(sparse.kron(self.makeQt(rho, T, diff=1), Qs).tocsc())
+        return Q, Q_fac, dQ
+
+    def setQ(self, par=None):
+        if par is None:
+            par = self.par
+        self.par = np.asarray(par, dtype="float64")
+        self.tau = self.par[-1]
+        self.Q, self.Q_fac, _ = self.makeQ(self.par, grad=False)
+        self.S = self.grid.getS()
+
+
 def sample(Q, S_full, n=1, seed=0, mu=None, tau=None, simple=True, nprod=None):
     """``Model.sample`` (``model.py:73-87``): ``S (P^T L^-T z + mu)`` (+ ``S[:, :N] z[:N]/sqrt(tau)``)."""
     N = Q.shape[0]

@@ -73,6 +73,8 @@ _SIGS = {
                                  c_int, ctypes.POINTER(ctypes.c_float), c_vp]),
     "spde_stencil_adjoint": (c_int, [c_int, c_int, c_int, c_dbl, c_dbl, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "spde_gemv_t": (c_int, [c_vp, c_vp, c_int, c_int, c_vp, c_vp]),
+    "spde_fill_kron": (c_int, [c_int, c_int, c_int, c_int, c_vp, c_dbl, c_dbl, c_dbl, c_vp, c_vp]),
+    "spde_kron_reduce": (c_int, [c_int, c_int, c_int, c_int, c_vp, c_dbl, c_dbl, c_dbl, c_vp, c_vp]),
     "spde_potrf_bench": (c_int, [c_int, c_int, c_int, c_int, ctypes.POINTER(ctypes.c_float), c_vp, c_vp]),
 }
 
@@ -110,13 +112,13 @@ def stream_ptr() -> int:
 class PlanHandle:
     """Owner of one ``spde_plan*`` (symbolic analysis + schedules + device workspaces)."""
 
-    def __init__(self, M: int, N: int, T: int, bc: int):
+    def __init__(self, M: int, N: int, T: int, bc: int, pat: int = 0):
         h = c_vp()
-        check(lib.spde_plan_create(M, N, T, bc, 0, ctypes.byref(h)))
+        check(lib.spde_plan_create(M, N, T, bc | (pat << 8), 0, ctypes.byref(h)))
         self.h = h
-        self.M, self.N, self.T, self.bc = M, N, T, bc
+        self.M, self.N, self.T, self.bc, self.pat = M, N, T, bc, pat
         self.n = int(lib.spde_plan_info(h, 0))
-        self.nslots = 25 if T == 1 else 43
+        self.nslots = 25 if T == 1 else (75 if pat == 1 else 43)
         self._perm = None
 
     def info(self, what: int) -> int:

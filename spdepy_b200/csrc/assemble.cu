@@ -340,6 +340,27 @@ __global__ void k_fill_spacetime(Geo g, const double *__restrict__ AtDA, const d
 }
 
 // ---------------------------------------------------------------------------------------------
+// K3c: separable space-time precision Q = Qt (x) Qs into the 75-slot layout (seperable_spatial_temporal2D.py:82,
+// sparse.kron: every entry is the single product Qt[t,t'] * Qs[k,k']).  Qt is the tridiagonal AR(1) precision with
+// diagonal (d0, d1, ..., d1, d0) and off-diagonal e (makeQt, :186-211).
+__global__ void k_fill_kron(Geo g, const double *__restrict__ Qs, double d0, double d1, double e, double *__restrict__ Q)
+{
+    const int Ns = g.M * g.N;
+    const size_t n = (size_t)Ns * g.T;
+    const size_t node = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (node >= n) return;
+    const int t = (int)(node / Ns), k = (int)(node % Ns);
+    const double dd = (t == 0 || t == g.T - 1) ? d0 : d1;
+#pragma unroll 5
+    for (int q = 0; q < 25; q++) {
+        const double v = Qs[(size_t)q * Ns + k];
+        Q[(size_t)q * n + node] = t > 0 ? e * v : 0.0;
+        Q[(size_t)(25 + q) * n + node] = dd * v;
+        Q[(size_t)(50 + q) * n + node] = t < g.T - 1 ? e * v : 0.0;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Adjoints of the two face-field stencils (transpose of k_ah_stencil / k_aw_stencil in derivative
 // mode).  Given GA9 = d S / d A9 they return d S / d (the eight tensor components the diffusion
 // stencil reads) and d S / d (dG of each face), so the gradient with respect to *all* spline
@@ -486,6 +507,18 @@ extern "C" int spde_atda(int M, int N, int bc, const double *d_A9, const double 
     if (bc == 2 && (M < 5 || N < 5)) { set_error("periodic meshes need M,N >= 5"); return SPDE_ERR_ARG; }
     Geo g{M, N, 1, bc};
     k_atda<<<cdiv(M * N, 128), 128, 0, (cudaStream_t)stream>>>(g, d_A9, d_kappa, kvar, V, mode, d_out25);
+    SPDE_LAUNCH_CHECK();
+    count_launch();
+    return SPDE_OK;
+}
+
+extern "C" int spde_fill_kron(int M, int N, int T, int bc, const double *d_Qs25, double d0, double d1, double e,
+                              double *d_Q75, void *stream)
+{
+    if (T < 2) { set_error("spde_fill_kron: T >= 2 required"); return SPDE_ERR_ARG; }
+    Geo g = geo_from_abi(M, N, T, bc | (1 << 8));
+    const size_t n = (size_t)M * N * T;
+    k_fill_kron<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(g, d_Qs25, d0, d1, e, d_Q75);
     SPDE_LAUNCH_CHECK();
     count_launch();
     return SPDE_OK;

@@ -34,6 +34,8 @@ void count_launch(int n = 1);   // bookkeeping for spde_launch_count (bench.py's
 // spat2Dtemp_regular_mesh.py:82-92.
 struct Geo {
     int M, N, T, bc;
+    int pat = 0;     // space-time pattern: 0 = 3x3 | 5x5 | 3x3 (advection-diffusion, 43 slots), 1 = 5x5 | 5x5 | 5x5 (Kronecker
+                     // Qt (x) Qs of the separable model, 75 slots, slot = (dt+1)*25 + (dj+2)*5 + (di+2))
     __host__ __device__ int Ns() const { return M * N; }
     // neighbour of cell (i,j) at offset (di,dj); returns -1 when it lies outside the mesh
     // (bc 1 and 3) or the wrapped cell (bc 2, AH_2D_b2.cpp:32-41).
@@ -47,11 +49,12 @@ struct Geo {
         }
         return jj * M + ii;
     }
-    __host__ __device__ int nslots() const { return T == 1 ? 25 : 43; }
+    __host__ __device__ int nslots() const { return T == 1 ? 25 : (pat == 1 ? 75 : 43); }
     // offsets of a precision slot (Q25 / Q43 layout, see spde_b200.h)
     __host__ __device__ void slot_offset(int slot, int &dt, int &dj, int &di) const {
         dt = 0;
         if (T == 1) { dj = slot / 5 - 2; di = slot % 5 - 2; }
+        else if (pat == 1) { dt = slot / 25 - 1; const int q = slot % 25; dj = q / 5 - 2; di = q % 5 - 2; }
         else if (slot < 9) { dt = -1; dj = slot / 3 - 1; di = slot % 3 - 1; }
         else if (slot < 34) { const int q = slot - 9; dj = q / 5 - 2; di = q % 5 - 2; }
         else { const int q = slot - 34; dt = 1; dj = q / 3 - 1; di = q % 3 - 1; }
@@ -70,5 +73,13 @@ struct Geo {
 };
 
 static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// C ABI convention: the boundary-condition argument carries the pattern in bits 8..15 (SPDE_PATTERN_KRON = 1 << 8)
+static inline Geo geo_from_abi(int M, int N, int T, int bc)
+{
+    Geo g{M, N, T, bc & 0xff};
+    g.pat = (bc >> 8) & 0xff;
+    return g;
+}
 
 }  // namespace spde

@@ -691,11 +691,13 @@ extern "C" long long spde_launch_count(int reset)
 
 extern "C" int spde_plan_create(int M, int N, int T, int bc, int max_rhs, spde_plan **out)
 {
-    if (M < 2 || N < 2 || T < 1 || bc < 1 || bc > 3 || !out) { set_error("spde_plan_create: bad arguments"); return SPDE_ERR_ARG; }
+    const Geo geo = geo_from_abi(M, N, T, bc);
+    bc = geo.bc;
+    if (M < 2 || N < 2 || T < 1 || bc < 1 || bc > 3 || geo.pat > 1 || !out) { set_error("spde_plan_create: bad arguments"); return SPDE_ERR_ARG; }
     if (bc == 2 && (M < 5 || N < 5)) { set_error("periodic meshes need M,N >= 5"); return SPDE_ERR_ARG; }
     Plan *p = new Plan();
     p->max_rhs = max_rhs;
-    p->sym.analyse(Geo{M, N, T, bc});
+    p->sym.analyse(geo);
     p->rel_base = (int64_t)p->sym.rows.size();
     p->build_layout();
     p->build_factor_program();

@@ -188,6 +188,27 @@ __global__ void k_adj_time_reduce(Geo g, const double *__restrict__ W, double *_
     }
 }
 
+// Separable model Q = Qt (x) Qs (seperable_spatial_temporal2D.py:82): weights W on the 75-slot pattern -> weights on Qs,
+//   Wd[q][k] = sum_t sum_dt Qt[t,t+dt] W[(dt+1)*25+q][(k,t)],   Qt tridiagonal with diagonal (d0, d1, ..., d1, d0), off-diagonal e
+__global__ void k_kron_reduce(Geo g, const double *__restrict__ W, double d0, double d1, double e, double *__restrict__ Wd)
+{
+    const int Ns = g.M * g.N;
+    const long long n = (long long)Ns * g.T;
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const int q = blockIdx.y;   // 0..24
+    if (k >= Ns) return;
+    double s = 0.0;
+    for (int t = 0; t < g.T; t++) {
+        const long long node = (long long)t * Ns + k;
+        const double dd = (t == 0 || t == g.T - 1) ? d0 : d1;
+        double v = dd * W[(long long)(25 + q) * n + node];
+        if (t > 0) v += e * W[(long long)q * n + node];
+        if (t < g.T - 1) v += e * W[(long long)(50 + q) * n + node];
+        s += v;
+    }
+    Wd[(long long)q * Ns + k] = s;
+}
+
 __device__ __forceinline__ double qs_val(double V, double kap) { const double As = V * kap; return (As * (1.0 / V)) * As; }
 
 // Phase 2: per cell c.  With k_s = c + off(s):
@@ -275,7 +296,7 @@ using namespace spde;
 
 extern "C" int spde_q_apply(int M, int N, int T, int bc, const double *d_Q, const double *d_X, int k, double *d_Y, void *stream)
 {
-    Geo g{M, N, T, bc};
+    Geo g = geo_from_abi(M, N, T, bc);
     const long long total = (long long)M * N * T * k;
     k_q_apply<<<(int)std::min<long long>((total + 255) / 256, 148 * 32), 256, 0, (cudaStream_t)stream>>>(g, d_Q, d_X, k, d_Y);
     SPDE_LAUNCH_CHECK();
@@ -300,7 +321,7 @@ extern "C" int spde_dot(const double *d_X, const double *d_Y, int64_t len, doubl
 extern "C" int spde_sddmm(int M, int N, int T, int bc, const double *d_X, const double *d_Y, int k, double alpha,
                           int accumulate, double *d_W, void *stream)
 {
-    Geo g{M, N, T, bc};
+    Geo g = geo_from_abi(M, N, T, bc);
     const long long n = (long long)M * N * T;
     if (k == 1) {
         k_sddmm1<<<(int)std::min<long long>((n + 255) / 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(g, d_X, d_Y, alpha, accumulate, d_W);
@@ -340,6 +361,17 @@ extern "C" int spde_assembly_adjoint(int M, int N, int T, int bc, const double *
     } else {
         k_adj_cell<<<cdiv(Ns, 128), 128, 0, st>>>(g, 0, d_W, nullptr, nullptr, nullptr, d_A9, d_kappa, kvar, V, 1.0, d_GA9, d_Gq);
     }
+    SPDE_LAUNCH_CHECK();
+    count_launch();
+    return SPDE_OK;
+}
+
+extern "C" int spde_kron_reduce(int M, int N, int T, int bc, const double *d_W75, double d0, double d1, double e,
+                                double *d_Wd25, void *stream)
+{
+    Geo g = geo_from_abi(M, N, T, bc | (1 << 8));
+    if (T < 2) { set_error("spde_kron_reduce: T >= 2 required"); return SPDE_ERR_ARG; }
+    k_kron_reduce<<<dim3(cdiv(M * N, 128), 25), 128, 0, (cudaStream_t)stream>>>(g, d_W75, d0, d1, e, d_Wd25);
     SPDE_LAUNCH_CHECK();
     count_launch();
     return SPDE_OK;

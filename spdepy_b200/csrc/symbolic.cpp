@@ -276,7 +276,7 @@ void Symbolic::analyse(const Geo &g, int leaf)
 {
     geo = g;
     n = g.M * g.N * g.T;
-    nslots = g.T == 1 ? 25 : 43;
+    nslots = g.nslots();
     if (leaf <= 0) {
         const char *env = getenv("SPDE_ND_LEAF");
         leaf = env ? atoi(env) : (g.T == 1 ? 32 : 64);

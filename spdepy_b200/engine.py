@@ -116,17 +116,18 @@ class Engine:
     _cache: dict = {}
 
     @classmethod
-    def get(cls, M: int, N: int, T: int, bc: int) -> "Engine":
-        key = (M, N, T, bc, torch.cuda.current_device() if torch.cuda.is_available() else -1)
+    def get(cls, M: int, N: int, T: int, bc: int, pat: int = 0) -> "Engine":
+        key = (M, N, T, bc, pat, torch.cuda.current_device() if torch.cuda.is_available() else -1)
         if key not in cls._cache:
-            cls._cache[key] = cls(M, N, T, bc)
+            cls._cache[key] = cls(M, N, T, bc, pat)
         return cls._cache[key]
 
-    def __init__(self, M: int, N: int, T: int, bc: int):
-        self.M, self.N, self.T, self.bc = M, N, T, bc
+    def __init__(self, M: int, N: int, T: int, bc: int, pat: int = 0):
+        self.M, self.N, self.T, self.bc, self.pat = M, N, T, bc, pat
+        self.bc_abi = bc | (pat << 8)          # pattern selector of the C ABI (SPDE_PATTERN_KRON)
         self.Ns = M * N
         self.n = self.Ns * T
-        self.nslots = 25 if T == 1 else 43
+        self.nslots = 25 if T == 1 else (75 if pat == 1 else 43)
         self._plan = None
         self._pattern = None
         self.serial = [0, 0]
@@ -134,13 +135,13 @@ class Engine:
     @property
     def plan(self) -> _lib.PlanHandle:
         if self._plan is None:
-            self._plan = _lib.PlanHandle(self.M, self.N, self.T, self.bc)
+            self._plan = _lib.PlanHandle(self.M, self.N, self.T, self.bc, self.pat)
         return self._plan
 
     @property
     def pattern(self) -> Pattern:
         if self._pattern is None:
-            self._pattern = Pattern(self.M, self.N, self.T, self.bc)
+            self._pattern = Pattern(self.M, self.N, self.T, self.bc, self.pat)
         return self._pattern
 
     # ------------------------------------------------------------------ assembly (K2, K3)
@@ -170,6 +171,18 @@ class Engine:
         out = torch.empty(43 * self.n, dtype=F64, device=_dev())
         check(lib.spde_fill_spacetime(self.M, self.N, self.T, self.bc, ptr(AtDA), ptr(A9), ptr(kappa), int(kappa.numel() > 1),
                                       V, ptr(Q0_25), sigma, dt, int(divide), ptr(out), _stream()))
+        return out
+
+    def fill_kron(self, Qs25: torch.Tensor, d0: float, d1: float, e: float) -> torch.Tensor:
+        """Q = Qt (x) Qs in the 75-slot layout; Qt = tridiag(diagonal (d0, d1, ..., d1, d0), off-diagonal e)."""
+        out = torch.empty(75 * self.n, dtype=F64, device=_dev())
+        check(lib.spde_fill_kron(self.M, self.N, self.T, self.bc, ptr(Qs25), float(d0), float(d1), float(e), ptr(out), _stream()))
+        return out
+
+    def kron_reduce(self, W75: torch.Tensor, d0: float, d1: float, e: float) -> torch.Tensor:
+        """Adjoint of :meth:`fill_kron` with respect to Qs (weights on the 25-slot spatial pattern)."""
+        out = torch.empty(25 * self.Ns, dtype=F64, device=_dev())
+        check(lib.spde_kron_reduce(self.M, self.N, self.T, self.bc, ptr(W75), float(d0), float(d1), float(e), ptr(out), _stream()))
         return out
 
     # ------------------------------------------------------------------ factor / solve / selinv (K4-K7, K10)
@@ -226,7 +239,7 @@ class Engine:
     # ------------------------------------------------------------------ reductions (K8, K9, K11)
     def q_apply(self, Q: torch.Tensor, X: torch.Tensor) -> torch.Tensor:
         Y = torch.empty_like(X)
-        check(lib.spde_q_apply(self.M, self.N, self.T, self.bc, ptr(Q), ptr(X), X.shape[1], ptr(Y), _stream()))
+        check(lib.spde_q_apply(self.M, self.N, self.T, self.bc_abi, ptr(Q), ptr(X), X.shape[1], ptr(Y), _stream()))
         return Y
 
     @staticmethod
@@ -263,7 +276,7 @@ class Engine:
         acc = W is not None
         if W is None:
             W = torch.zeros(self.nslots * self.n, dtype=F64, device=_dev())
-        check(lib.spde_sddmm(self.M, self.N, self.T, self.bc, ptr(X), ptr(Y), X.shape[1], float(alpha), int(acc), ptr(W), _stream()))
+        check(lib.spde_sddmm(self.M, self.N, self.T, self.bc_abi, ptr(X), ptr(Y), X.shape[1], float(alpha), int(acc), ptr(W), _stream()))
         return W
 
     def assembly_adjoint(self, W, A9, kappa, V, sigma, dt, timed: bool):

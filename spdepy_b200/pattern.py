@@ -13,11 +13,15 @@ import numpy as np
 from scipy import sparse
 
 
-def slot_offsets(T: int):
+def slot_offsets(T: int, pat: int = 0):
     """(dt, dj, di) of every slot; mirrors ``Geo::slot_offset`` in ``csrc/common.cuh``."""
     if T == 1:
         q = np.arange(25)
         return np.zeros(25, np.int64), q // 5 - 2, q % 5 - 2
+    if pat == 1:        # Kronecker pattern of the separable model: 5x5 blocks to t-1, t, t+1
+        s = np.arange(75)
+        q = s % 25
+        return s // 25 - 1, q // 5 - 2, q % 5 - 2
     dt = np.concatenate([np.full(9, -1), np.zeros(25, np.int64), np.full(9, 1)])
     q3, q5 = np.arange(9), np.arange(25)
     dj = np.concatenate([q3 // 3 - 1, q5 // 5 - 2, q3 // 3 - 1])
@@ -26,15 +30,15 @@ def slot_offsets(T: int):
 
 
 class Pattern:
-    def __init__(self, M: int, N: int, T: int, bc: int):
-        self.M, self.N, self.T, self.bc = M, N, T, bc
+    def __init__(self, M: int, N: int, T: int, bc: int, pat: int = 0):
+        self.M, self.N, self.T, self.bc, self.pat = M, N, T, bc, pat
         self.Ns = M * N
         self.n = self.Ns * T
-        self.nslots = 25 if T == 1 else 43
+        self.nslots = 25 if T == 1 else (75 if pat == 1 else 43)
         node = np.arange(self.n, dtype=np.int64)
         t, k = node // self.Ns, node % self.Ns
         i, j = k % M, k // M
-        dt, dj, di = slot_offsets(T)
+        dt, dj, di = slot_offsets(T, pat)
         ii = i[None, :] + di[:, None]
         jj = j[None, :] + dj[:, None]
         tt = t[None, :] + dt[:, None]

@@ -94,5 +94,10 @@ def spde_init(model, grid, parameters=None, ani=True, ha=True, bc=3, mod0=None):
                 return cls(par=parameters, grid=grid, bc=bc, mod0=mod0)
             return cls(par=parameters, grid=grid, bc=bc)
     if model in _NEXT or model in _NEXT.values():
-        raise NotImplementedError("model family %r is outside this round's hot-path scope (SURVEY.md section 8f)" % (model,))
+        if ha or not ani:
+            raise NotImplementedError("seperable-spatial-temporal: only the anisotropic class is wired; the reference's ha / "
+                                      "idiffusion variants build Qt with a hard-coded range(10) "
+                                      "(seperable_spatial_temporal_ha2D.py:205-211)")
+        from .separable import SeperableSpatialTemporal2D
+        return SeperableSpatialTemporal2D(par=parameters, grid=grid, bc=bc)
     raise AssertionError("Model not implemented")

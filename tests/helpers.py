@@ -56,6 +56,8 @@ def make_grids(d):
 def make_oracle(d):
     import spde_oracle as so
     g, g0 = make_grids(d)
+    if d["spde"] == "seperable-spatial-temporal":
+        return so.OracleSeparable(g, bc=d["bc"])
     mod0 = None
     if g0 is not None:
         mod0 = so.OracleSPDE(spec_key(d["mod0_spde"], d["ha"], d["ani"]), g0, bc=d["bc"], par=d["mod0_par"])

@@ -100,8 +100,7 @@ def test_makeQ_against_reference_golden(name):
     if "ww" in d and d["ww"].size:
         mod.mod.ww = d["ww"]
     assert mod.mod.type == d["type"]
-    Q, fac, _ = mod.mod.makeQ(d["par"], grad=False)
-    Q = canon(Q)
+    Q = canon(mod.mod.makeQ(d["par"], grad=False)[0])        # (Q, Q_fac, None); the separable class returns (Q, Q_fac)
     ref = d["Q"]
     assert np.array_equal(Q.indptr, ref.indptr) and np.array_equal(Q.indices, ref.indices)
     rel = np.abs(Q.data - ref.data) / np.abs(ref.data)
