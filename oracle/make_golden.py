@@ -46,6 +46,9 @@ CASES = [
     ("cad_ani_bc1_q0", "cov-advection-diffusion", False, True, 1, (8, 7, 3), None, "whittle-matern", True),
     ("cavd_ha_bc3", "cov-advection-var-diffusion", True, True, 3, (8, 7, 3), None, "whittle-matern", False),
     ("vavd_iso_bc3_q0", "var-advection-var-diffusion", False, False, 3, (8, 7, 3), None, "whittle-matern", True),
+    # var-Whittle-Matern classes without makeQ in the reference (inline assembly in logLike)
+    ("varwm_iso_bc3", "var-whittle-matern", False, False, 3, (11, 9, None), None, None, False),
+    ("varwm_ha_bc1_ext", "var-whittle-matern", True, True, 1, (10, 9, None), 2, None, False),
     # separable space-time model Q = Qt (x) Qs (the reference ignores mod0 for this family)
     ("sep_ani_bc3", "seperable-spatial-temporal", False, True, 3, (8, 7, 4), None, "whittle-matern", False),
     ("sep_ani_bc1_ext", "seperable-spatial-temporal", False, True, 1, (7, 6, 3), 1, "whittle-matern", False),
@@ -117,8 +120,14 @@ def run_case(case):
     # intermediate quantities (recomputed exactly as logLike does, advection_diffusion2D.py:190-198)
     from sksparse.cholmod import cholesky
     tau = np.exp(par[-1])
-    res = mod.mod.makeQ(par=par, grad=False)          # (Q, Q_fac, None) or, for the separable class, (Q, Q_fac)
-    Qm, Qf = res[0], res[1]
+    if hasattr(mod.mod, "makeQ"):
+        res = mod.mod.makeQ(par=par, grad=False)          # (Q, Q_fac, None) or, for the separable class, (Q, Q_fac)
+        Qm, Qf = res[0], res[1]
+    else:                                                 # var-whittle-matern iso / ha: setQ is the only assembly entry
+        S_obs = mod.mod.S                                 # setQ resets S to the full selection matrix
+        mod.mod.setQ(par=par)
+        Qm, Qf = mod.mod.Q, mod.mod.Q_fac
+        mod.mod.S = S_obs
     S = mod.mod.S
     Qc = Qm + S.T @ S * tau
     Qcf = cholesky(Qc)

@@ -51,6 +51,9 @@ SPECS = {
     "whittle-matern-anisotropic-2D": Spec("whittle-matern-anisotropic-2D", False, False, "aniso", False, None),
     "whittle-matern-ha-2D": Spec("whittle-matern-ha-2D", False, False, "ha", False, None),
     "var-whittle-matern-anisotropic-2D": Spec("var-whittle-matern-anisotropic-2D", False, True, "aniso", True, None),
+    # (assembled inline in the reference's logLike: var_whittle_matern2D.py:92-104, var_whittle_matern_ha2D.py:126-140)
+    "var-whittle-matern-isotropic-2D": Spec("var-whittle-matern-isotropic-2D", False, True, "iso", True, None),
+    "var-whittle-matern-ha-2D": Spec("var-whittle-matern-ha-2D", False, True, "ha", True, None),
     # advection-diffusion (spdes/__init__.py:25-35)
     "advection-diffusion-2D": Spec("advection-diffusion-2D", True, False, "aniso", False, "const"),
     "advection-idiffusion-2D": Spec("advection-idiffusion-2D", True, False, "iso", False, "const"),

@@ -19,6 +19,12 @@ WhittleMaternAnisotropic2D = _cls("WhittleMaternAnisotropic2D", "whittle-matern-
 WhittleMaternHa2D = _cls("WhittleMaternHa2D", "whittle-matern-ha-2D", Hkind="ha", default_own=(-1, -1, 0.1, 0.1))
 VarWhittleMaternAnisotropic2D = _cls("VarWhittleMaternAnisotropic2D", "var-whittle-matern-anisotropic-2D", kvar=True,
                                      Hkind="aniso", Hvar=True, default_own=([-1] * N9, [-1] * N9, [0.1] * N9, [0.1] * N9))
+# (the reference's isotropic / half-angle var-Whittle-Matern classes assemble inline in logLike, var_whittle_matern2D.py:92-104,
+#  var_whittle_matern_ha2D.py:126-140; here they get the common makeQ as well)
+VarWhittleMatern2D = _cls("VarWhittleMatern2D", "var-whittle-matern-isotropic-2D", kvar=True, Hkind="iso", Hvar=True,
+                          default_own=([-1] * N9, [-1] * N9))
+VarWhittleMaternHa2D = _cls("VarWhittleMaternHa2D", "var-whittle-matern-ha-2D", kvar=True, Hkind="ha", Hvar=True,
+                            default_own=([-1] * N9, [-1] * N9, [0.1] * N9, [0.1] * N9))
 # advection-diffusion, constant coefficients (advection_*diffusion2D.py)
 AdvectionDiffusion2D = _cls("AdvectionDiffusion2D", "advection-diffusion-2D", timed=True, Hkind="aniso", wkind="const",
                             aflav=1, default_own=(-1, -1, 0.01, 0.01, 0.01, 0.01, 0))
@@ -70,7 +76,7 @@ CovAdvectionVarHaDiffusion2D = _cls("CovAdvectionVarHaDiffusion2D", "cov-advecti
 _TABLE = {
     # model id -> (ha class, anisotropic class, isotropic class)
     ("whittle-matern", 1): (WhittleMaternHa2D, WhittleMaternAnisotropic2D, WhittleMatern2D),
-    ("var-whittle-matern", -1): (None, VarWhittleMaternAnisotropic2D, None),
+    ("var-whittle-matern", -1): (VarWhittleMaternHa2D, VarWhittleMaternAnisotropic2D, VarWhittleMatern2D),
     ("advection-diffusion", 2): (AdvectionHaDiffusion2D, AdvectionDiffusion2D, AdvectionIDiffusion2D),
     ("advection-var-diffusion", 3): (AdvectionVarHaDiffusion2D, AdvectionVarDiffusion2D, AdvectionVarIDiffusion2D),
     ("cov-advection-diffusion", 4): (CovAdvectionHaDiffusion2D, CovAdvectionDiffusion2D, CovAdvectionIDiffusion2D),
