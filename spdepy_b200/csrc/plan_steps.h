@@ -1,0 +1,463 @@
+// plan_steps.h -- building blocks shared by the schedule builders (plan_build.cpp: whole-tree, in-core
+// schedules; ooc.cpp: per-segment schedules of the streamed evaluator): the level builder that merges
+// per-supernode step sequences into grouped launches, and the step sequence of one supernode for the
+// factorisation, the triangular solves and the Takahashi recursion.
+#pragma once
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+
+#include "plan.h"
+
+namespace spde {
+
+static inline int up2(int x) { return x + (x & 1); }
+
+static constexpr int CFG_BM[3] = {128, 128, 64};
+static constexpr int CFG_BN[3] = {128, 64, 64};
+
+// tile configuration of a grouped launch: the largest tile that still gives >= 2 CTAs per SM
+static constexpr int kSMs = 148;
+static inline long long count_tiles(const GemmTask &t, int cfg)
+{
+    const int BM = CFG_BM[cfg], BN = CFG_BN[cfg];
+    const int tm = (t.M + BM - 1) / BM, tn = (t.N + BN - 1) / BN;
+    if (!(t.flags & GF_LOWER)) return (long long)tm * tn;
+    long long c = 0;
+    for (int tj = 0; tj < tn; tj++)
+        for (int ti = 0; ti < tm; ti++) c += !((ti + 1) * BM - 1 < tj * BN);
+    return c;
+}
+
+struct Step {
+    int kind;            // LaunchKind
+    int variant;         // GEMM: cfg*4 + akmaj*2 + bkmaj
+    int g0, gn;          // range in the level's GEMM pool
+    PotrfTask p;
+    WtwTask w;
+};
+
+struct LevelBuilder {
+    Program &prog;
+    std::vector<GemmTask> pool;
+    std::vector<std::vector<Step>> seq;   // one sequence per supernode of the level
+    explicit LevelBuilder(Program &p) : prog(p) {}
+
+    GemmTask task(int sa, long long a, int lda, int sb, long long b, int ldb, int sc, long long c, int ldc,
+                  int M, int N, int K, int flags)
+    {
+        GemmTask t;
+        memset(&t, 0, sizeof t);
+        t.a = a; t.b = b; t.c = c; t.c2 = 0;
+        t.lda = lda; t.ldb = ldb; t.ldc = ldc;
+        t.M = M; t.N = N; t.K = K;
+        t.flags = flags | sa | (sb << 3) | (sc << 6);
+        return t;
+    }
+    void add_gemm(std::vector<Step> &s, const GemmTask &t, bool akmaj, bool bkmaj, int cfg = -1)
+    {
+        if (t.M <= 0 || t.N <= 0 || t.K <= 0) return;
+        Step st;
+        memset(&st, 0, sizeof st);
+        st.kind = LK_GEMM;
+        // bits 0-1: operand layouts; bits 2-3: forced tile config + 1 (0 = choose per launch)
+        st.variant = ((cfg + 1) << 2) + (akmaj ? 2 : 0) + (bkmaj ? 1 : 0);
+        st.g0 = (int)pool.size();
+        st.gn = 1;
+        pool.push_back(t);
+        s.push_back(st);
+    }
+    // small-M (k <= 4 right-hand sides) matrix-vector step; variant = B layout
+    void add_gemv(std::vector<Step> &s, const GemmTask &t, bool bkmaj)
+    {
+        if (t.M <= 0 || t.N <= 0 || t.K <= 0) return;
+        Step st;
+        memset(&st, 0, sizeof st);
+        st.kind = LK_GEMV;
+        st.variant = bkmaj ? 1 : 0;
+        st.g0 = (int)pool.size();
+        st.gn = 1;
+        pool.push_back(t);
+        s.push_back(st);
+    }
+    // dense step of a solve: tensor-core GEMM, or the matrix-vector kernel when there are <= 4 columns
+    void add_solve(std::vector<Step> &s, const GemmTask &t, bool bkmaj)
+    {
+        if (t.M <= 4) add_gemv(s, t, bkmaj);
+        else add_gemm(s, t, false, bkmaj);
+    }
+    void emit_gemv_launch(int bk, const std::vector<const Step *> &steps)
+    {
+        const int TN = bk ? 64 : 256, KC = bk ? GEMV_KC_K : GEMV_KC_N;
+        Launch L;
+        memset(&L, 0, sizeof L);
+        L.kind = LK_GEMV;
+        L.variant = bk;
+        L.task0 = (int64_t)prog.gemm.size();
+        L.tile0 = (int64_t)prog.tiles.size();
+        for (const Step *st : steps)
+            for (int g = st->g0; g < st->g0 + st->gn; g++) {
+                const GemmTask &t = pool[g];
+                const int id = (int)(prog.gemm.size() - L.task0);
+                prog.gemm.push_back(t);
+                const int tn = (t.N + TN - 1) / TN, tk = (t.K + KC - 1) / KC;
+                for (int kc = 0; kc < tk; kc++)
+                    for (int tj = 0; tj < tn; tj++) prog.tiles.push_back(TileRef{id, kc, tj, 0});
+                prog.flops += 2.0 * t.M * t.N * t.K;
+            }
+        L.ntasks = (int)(prog.gemm.size() - L.task0);
+        L.ntiles = (int)(prog.tiles.size() - L.tile0);
+        if (L.ntiles > 0) prog.launches.push_back(L);
+    }
+
+    // append `t` to the previous GEMM step (same variant) instead of opening a new step
+    void join_gemm(std::vector<Step> &s, const GemmTask &t)
+    {
+        if (t.M <= 0 || t.N <= 0 || t.K <= 0) return;
+        pool.push_back(t);
+        s.back().gn++;
+    }
+
+    void emit_gemm_launch(int key, const std::vector<const Step *> &steps)
+    {
+        int cfg = (key >> 2) - 1;
+        if (cfg < 0) {
+            // Tile shape: measured on B200 (tools/tile_sweep.py, profiles/r1_tile_sweep.txt) the 64x64 tile with
+            // four warps (3-4 resident CTAs per SM) matches or beats the larger tiles on every problem shape of the
+            // schedules -- square, K = 512 panels and skinny N = 64 -- so it is used for all grouped launches
+            // (k-tile 32 with a 2-stage ring: +1-2 % on full launches, +16 % on under-filled skinny ones).
+            const char *env = getenv("SPDE_TILE");
+            cfg = env ? atoi(env) : 2;
+            if (cfg < 0 || cfg > 2) cfg = 2;
+        }
+        const int variant = cfg * 4 + (key & 3);
+        const int BM = CFG_BM[cfg], BN = CFG_BN[cfg];
+        Launch L;
+        memset(&L, 0, sizeof L);
+        L.kind = LK_GEMM;
+        L.variant = variant;
+        L.task0 = (int64_t)prog.gemm.size();
+        L.tile0 = (int64_t)prog.tiles.size();
+        // longest tiles first: CTAs are dispatched in tile order, so the long-K tiles of the big fronts start
+        // early and the short ones fill the tail (LPT packing of one grouped launch)
+        std::vector<int> order;
+        for (const Step *st : steps)
+            for (int g = st->g0; g < st->g0 + st->gn; g++) order.push_back(g);
+        std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return pool[x].K > pool[y].K; });
+        for (int g : order) {
+            {
+                const GemmTask &t = pool[g];
+                const int id = (int)(prog.gemm.size() - L.task0);
+                prog.gemm.push_back(t);
+                const int tm = (t.M + BM - 1) / BM, tn = (t.N + BN - 1) / BN;
+                const bool lower = t.flags & GF_LOWER;
+                for (int tj = 0; tj < tn; tj++)
+                    for (int ti = 0; ti < tm; ti++) {
+                        if (lower && (ti + 1) * BM - 1 < tj * BN) continue;
+                        prog.tiles.push_back(TileRef{id, ti, tj, 0});
+                    }
+                prog.flops += 2.0 * t.M * t.N * t.K * (lower ? 0.5 : 1.0);
+            }
+        }
+        L.ntasks = (int)(prog.gemm.size() - L.task0);
+        L.ntiles = (int)(prog.tiles.size() - L.tile0);
+        if (L.ntiles > 0) prog.launches.push_back(L);
+    }
+
+    // merge the per-supernode sequences into grouped launches
+    void flush()
+    {
+        const size_t m = seq.size();
+        std::vector<size_t> head(m, 0);
+        size_t remaining = 0;
+        for (auto &s : seq) remaining += s.size();
+        while (remaining) {
+            // pick the (kind, variant) shared by most heads
+            std::map<std::pair<int, int>, int> votes;
+            for (size_t i = 0; i < m; i++)
+                if (head[i] < seq[i].size()) votes[{seq[i][head[i]].kind, (seq[i][head[i]].kind == LK_GEMM || seq[i][head[i]].kind == LK_GEMV) ? seq[i][head[i]].variant : 0}]++;
+            std::pair<int, int> best{-1, -1};
+            int bv = -1;
+            for (auto &kv : votes) if (kv.second > bv) { bv = kv.second; best = kv.first; }
+            std::vector<const Step *> chosen;
+            for (size_t i = 0; i < m; i++) {
+                if (head[i] >= seq[i].size()) continue;
+                const Step &st = seq[i][head[i]];
+                if (st.kind != best.first) continue;
+                if ((st.kind == LK_GEMM || st.kind == LK_GEMV) && st.variant != best.second) continue;
+                chosen.push_back(&st);
+                head[i]++;
+                remaining--;
+            }
+            if (best.first == LK_GEMM) {
+                emit_gemm_launch(best.second, chosen);
+            } else if (best.first == LK_GEMV) {
+                emit_gemv_launch(best.second, chosen);
+            } else if (best.first == LK_POTRF) {
+                Launch L;
+                memset(&L, 0, sizeof L);
+                L.kind = LK_POTRF;
+                L.task0 = (int64_t)prog.potrf.size();
+                for (const Step *st : chosen) prog.potrf.push_back(st->p);
+                L.ntasks = (int)chosen.size();
+                prog.launches.push_back(L);
+            } else if (best.first == LK_WTW) {
+                Launch L;
+                memset(&L, 0, sizeof L);
+                L.kind = LK_WTW;
+                L.task0 = (int64_t)prog.wtw.size();
+                for (const Step *st : chosen) prog.wtw.push_back(st->w);
+                L.ntasks = (int)chosen.size();
+                prog.launches.push_back(L);
+            }
+        }
+        seq.clear();
+        pool.clear();
+    }
+};
+
+static inline void zero_launch(Program &p, int space, int64_t a0, int64_t a1)
+{
+    if (a1 <= a0) return;
+    Launch L;
+    memset(&L, 0, sizeof L);
+    L.kind = LK_ZERO;
+    L.variant = space;
+    L.a0 = a0;
+    L.a1 = a1;
+    p.launches.push_back(L);
+}
+
+// spaces: 0 L, 1 arena0, 2 arena1, 3 dinv, 4 X, 5 ybuf, 6 zarena0, 7 zarena1
+enum { SP_L = 0, SP_AR0 = 1, SP_DINV = 3, SP_X = 4, SP_Y = 5, SP_Z0 = 6 };
+
+// extend-add task of one child update matrix (compact nr x nr, leading dimension lds, at `src` of space
+// `src_space`) into its parent's panel / update matrix; appends the task and its 32x32 lower tiles to launch L
+static inline void push_ext_task(Program &P, Launch &L, long long src, int lds, int nr, int64_t rows_off, int64_t rel_base,
+                                 const SNode &p, int src_space, int dst_space)
+{
+    if (nr == 0) return;
+    ExtTask e;
+    memset(&e, 0, sizeof e);
+    e.src = src; e.lds = lds; e.nr = nr;
+    e.ppanel = p.panel; e.pld = p.ld; e.pnc = p.nc; e.pncp = p.ncp;
+    e.pupd = p.upd; e.pldu = p.ldu;
+    e.rel = (int)(rel_base + rows_off);
+    e.src_space = src_space; e.dst_space = dst_space;
+    const int id = (int)(P.ext.size() - L.task0);
+    P.ext.push_back(e);
+    const int nt = (nr + 31) / 32;
+    for (int tj = 0; tj < nt; tj++)
+        for (int ti = tj; ti < nt; ti++) P.tiles.push_back(TileRef{id, ti, tj, 0});
+}
+
+// gather task of the selected inverse: the nr x nr block of the parent's front addressed by the relative
+// indices -> block (ncp.., ncp..) of the matrix at `dst` (leading dimension ldd)
+static inline void push_gather_task(Program &P, Launch &L, long long dst, int ldd, int ncp, int nr, long long src, int lds,
+                                    int pnc, int pncp, int64_t rel, int src_space, int dst_space)
+{
+    if (nr == 0) return;
+    GatherTask g;
+    memset(&g, 0, sizeof g);
+    g.dst = dst; g.ldd = ldd; g.ncp = ncp; g.nr = nr;
+    g.src = src; g.lds = lds; g.pnc = pnc; g.pncp = pncp;
+    g.rel = (int)rel;
+    g.src_space = src_space; g.dst_space = dst_space;
+    const int id = (int)(P.gather.size() - L.task0);
+    P.gather.push_back(g);
+    const int nt = (nr + 31) / 32;
+    for (int tj = 0; tj < nt; tj++)
+        for (int ti = 0; ti < nt; ti++) P.tiles.push_back(TileRef{id, ti, tj, 0});
+}
+
+// Dense partial Cholesky of one front (panel already assembled): left-looking GEMM inside an outer block of
+// `outer` 64-column blocks, 64x64 POTRF with explicit inverse, TRSM-as-GEMM with that inverse, right-looking GEMM
+// beyond the outer block, one SYRK of the update matrix with K = all pivot columns.
+static inline void factor_node_steps(LevelBuilder &B, const SNode &x, int sp_u, int outer, std::vector<Step> &q)
+{
+    const int mrows = x.ncp + x.nr;     // panel rows in use (the gap row of an odd nc is zero)
+    for (int P0 = 0; P0 < x.nblk; P0 += outer) {
+        const int P1 = std::min(P0 + outer, x.nblk);
+        const int cP = P0 * NB;
+        for (int p = P0; p < P1; p++) {
+            const int c0 = p * NB, b = std::min(NB, x.nc - c0);
+            if (p > P0) {
+                // left-looking update of block column p from the inner blocks of this outer block
+                const int K = c0 - cP;
+                B.add_gemm(q, B.task(SP_L, x.panel + c0 + (int64_t)cP * x.ld, x.ld,
+                                     SP_L, x.panel + c0 + (int64_t)cP * x.ld, x.ld,
+                                     SP_L, x.panel + c0 + (int64_t)c0 * x.ld, x.ld,
+                                     mrows - c0, b, K, GF_NEG), false, false);
+            }
+            Step st;
+            memset(&st, 0, sizeof st);
+            st.kind = LK_POTRF;
+            st.p.blk = x.panel + c0 + (int64_t)c0 * x.ld;
+            st.p.dinv = x.dinv + (int64_t)p * NB * NB;
+            st.p.ld = x.ld; st.p.b = b; st.p.col0 = x.first + c0;
+            q.push_back(st);
+            // rows below the diagonal block: L = A * W^T, in place
+            const int r0 = (p == x.nblk - 1) ? x.ncp : c0 + NB;
+            B.add_gemm(q, B.task(SP_L, x.panel + r0 + (int64_t)c0 * x.ld, x.ld,
+                                 SP_DINV, st.p.dinv, NB,
+                                 SP_L, x.panel + r0 + (int64_t)c0 * x.ld, x.ld,
+                                 mrows - r0, b, b, GF_BETA0), false, false);
+        }
+        if (P1 < x.nblk) {
+            // right-looking update of the panel columns beyond this outer block
+            const int cR = P1 * NB, K = cR - cP;
+            B.add_gemm(q, B.task(SP_L, x.panel + cR + (int64_t)cP * x.ld, x.ld,
+                                 SP_L, x.panel + cR + (int64_t)cP * x.ld, x.ld,
+                                 SP_L, x.panel + cR + (int64_t)cR * x.ld, x.ld,
+                                 mrows - cR, x.nc - cR, K, GF_NEG | GF_LOWER), false, false);
+        }
+    }
+    if (x.nr > 0) {
+        // update matrix U -= L21 L21^T (lower), K = all pivot columns
+        B.add_gemm(q, B.task(SP_L, x.panel + x.ncp, x.ld, SP_L, x.panel + x.ncp, x.ld,
+                             sp_u, x.upd, x.ldu, x.nr, x.nr, x.nc, GF_NEG | GF_LOWER), false, false);
+    }
+}
+
+// Forward substitution L y = b on the columns of one supernode (X is kp x n, k-major, permuted order).
+static inline void fsolve_node_steps(LevelBuilder &B, const SNode &x, int k, int kp, bool blocked, int OUTER, std::vector<Step> &q)
+{
+    const int64_t xs = (int64_t)x.first * kp;
+    // Many right-hand sides (tensor-core path): two-level blocking as in the factorisation -- inside an
+    // outer block of OUTER*64 pivot columns the update after each 64-block stays inside the outer block
+    // (N <= 448), and one K = 512 update per outer block reaches the remaining pivot columns.  A few
+    // right-hand sides (matrix-vector path): one update of all remaining columns per 64-block.
+    const int outer = blocked ? OUTER : x.nblk;
+    for (int P0 = 0; P0 < x.nblk; P0 += outer) {
+        const int P1 = std::min(P0 + outer, x.nblk);
+        const int cEnd = std::min(P1 * NB, x.nc);
+        for (int p = P0; p < P1; p++) {
+            const int c0 = p * NB, b = std::min(NB, x.nc - c0);
+            // y_p = x_p W_p^T (in place)
+            B.add_solve(q, B.task(SP_X, xs + (int64_t)c0 * kp, kp, SP_DINV, x.dinv + (int64_t)p * NB * NB, NB,
+                                 SP_X, xs + (int64_t)c0 * kp, kp, k, b, b, GF_BETA0), false);
+            // remaining pivot columns of this outer block
+            const int rest = cEnd - c0 - b;
+            if (rest > 0)
+                B.add_solve(q, B.task(SP_X, xs + (int64_t)c0 * kp, kp,
+                                     SP_L, x.panel + (c0 + b) + (int64_t)c0 * x.ld, x.ld,
+                                     SP_X, xs + (int64_t)(c0 + b) * kp, kp, k, rest, b, GF_NEG), false);
+        }
+        if (cEnd < x.nc) {
+            const int cP = P0 * NB;
+            B.add_solve(q, B.task(SP_X, xs + (int64_t)cP * kp, kp,
+                                 SP_L, x.panel + cEnd + (int64_t)cP * x.ld, x.ld,
+                                 SP_X, xs + (int64_t)cEnd * kp, kp, k, x.nc - cEnd, cEnd - cP, GF_NEG), false);
+        }
+    }
+    if (x.nr > 0) {
+        GemmTask t = B.task(SP_X, xs, kp, SP_L, x.panel + x.ncp, x.ld, SP_X, 0, kp, k, x.nr, x.nc,
+                            GF_NEG | GF_SCATTER_C | GF_ATOMIC);
+        t.cidx = (int)x.rows;
+        B.add_solve(q, t, false);
+    }
+}
+
+// Back substitution L^T x = y on the columns of one supernode.
+static inline void bsolve_node_steps(LevelBuilder &B, const SNode &x, int k, int kp, bool blocked, int OUTER, std::vector<Step> &q)
+{
+    const int64_t xs = (int64_t)x.first * kp;
+    if (x.nr > 0) {
+        // x_s -= X[rows below] * L21   (columns of X gathered through the row list)
+        GemmTask t = B.task(SP_X, 0, kp, SP_L, x.panel + x.ncp, x.ld, SP_X, xs, kp, k, x.nc, x.nr,
+                            GF_NEG | GF_GATHER_A);
+        t.aidx = (int)x.rows;
+        B.add_solve(q, t, true);
+    }
+    // Many right-hand sides: left-looking only inside an outer block (K <= 448), then one right-looking
+    // K = 512 update of ALL earlier pivot columns per outer block -- a long-K product on a 64-column block
+    // would have k/64 tiles for the whole machine (measured: 1024 samples on C3 at ~5 TFLOP/s).
+    const int outer = blocked ? OUTER : x.nblk;
+    const int nouter = (x.nblk + outer - 1) / outer;
+    for (int o = nouter - 1; o >= 0; o--) {
+        const int P0 = o * outer, P1 = std::min(P0 + outer, x.nblk);
+        const int cEnd = std::min(P1 * NB, x.nc), cP = P0 * NB;
+        for (int p = P1 - 1; p >= P0; p--) {
+            const int c0 = p * NB, b = std::min(NB, x.nc - c0);
+            const int later = cEnd - c0 - b;
+            if (later > 0)   // x_p -= X[later pivot columns of the outer block] * L[later, p]
+                B.add_solve(q, B.task(SP_X, xs + (int64_t)(c0 + b) * kp, kp,
+                                     SP_L, x.panel + (c0 + b) + (int64_t)c0 * x.ld, x.ld,
+                                     SP_X, xs + (int64_t)c0 * kp, kp, k, b, later, GF_NEG), true);
+            // x_p = y_p W_p (in place)
+            B.add_solve(q, B.task(SP_X, xs + (int64_t)c0 * kp, kp, SP_DINV, x.dinv + (int64_t)p * NB * NB, NB,
+                                 SP_X, xs + (int64_t)c0 * kp, kp, k, b, b, GF_BETA0), true);
+        }
+        if (cP > 0)          // X[earlier pivot columns] -= X[outer block] * L[outer block, earlier]
+            B.add_solve(q, B.task(SP_X, xs + (int64_t)cP * kp, kp,
+                                 SP_L, x.panel + cP, x.ld,
+                                 SP_X, xs, kp, k, cP, cEnd - cP, GF_NEG), true);
+    }
+}
+
+// Takahashi recursion on one front whose trailing block Z[below,below] is in place: block columns from last to
+// first.  Y = scratch of ld x 64 doubles at offset Y of the Y space.
+static inline void selinv_node_steps(LevelBuilder &B, const SNode &x, int sp_z, int64_t Y, int splitk_min, int kchunk,
+                                     std::vector<Step> &q)
+{
+    const int mrows = x.ncp + x.nr;
+    const int64_t F = x.front;
+    for (int p = x.nblk - 1; p >= 0; p--) {
+        const int c0 = p * NB, b = std::min(NB, x.nc - c0);
+        const int r0 = (p == x.nblk - 1) ? x.ncp : c0 + NB;
+        const int mb = mrows - r0;
+        const int64_t W = x.dinv + (int64_t)p * NB * NB;
+        const int ldy = up2(std::max(mb, 2));
+        // Z_pp = W^T W  (+ correction below)
+        Step st;
+        memset(&st, 0, sizeof st);
+        st.kind = LK_WTW;
+        st.w.w = W; st.w.dst = F + c0 + (int64_t)c0 * x.ld; st.w.ldd = x.ld; st.w.b = b; st.w.space = sp_z;
+        q.push_back(st);
+        if (mb <= 0) continue;
+        // Y = L[below,p] * W
+        B.add_gemm(q, B.task(SP_L, x.panel + r0 + (int64_t)c0 * x.ld, x.ld, SP_DINV, W, NB,
+                             SP_Y, Y, ldy, mb, b, b, GF_BETA0), false, true);
+        // Z[below,p] = -Z[below,below] * Y   (and its transpose into the row block)
+        // Skinny product (N <= 64): for the big fronts near the root there are fewer row tiles than
+        // SMs, so K is split into chunks that accumulate atomically into the (still zero) block.
+        // The K chunks also bound the duration of one tile: a launch ends with a partially filled wave of
+        // CTAs, and with K = mb in the thousands one 64x64 tile runs for hundreds of microseconds
+        // (profiles/: mean selinv launch ~0.5 ms), so short chunks keep the tail of every launch short.
+        int nchunk = 1;
+        if (mb >= splitk_min) {
+            const int rowtiles = (mb + 127) / 128;
+            nchunk = std::max(1, std::min((2 * kSMs + rowtiles - 1) / rowtiles, mb / (splitk_min / 4)));
+        }
+        if (kchunk > 0 && mb > kchunk + kchunk / 2) nchunk = std::max(nchunk, (mb + kchunk - 1) / kchunk);
+        int clen = (mb + nchunk - 1) / nchunk;
+        clen += clen & 1;
+        for (int k0 = 0, ci = 0; k0 < mb; k0 += clen, ci++) {
+            GemmTask t = B.task(sp_z, F + r0 + (int64_t)(r0 + k0) * x.ld, x.ld, SP_Y, Y + k0, ldy,
+                                sp_z, F + r0 + (int64_t)c0 * x.ld, x.ld, mb, b, std::min(clen, mb - k0),
+                                GF_NEG | GF_UPPER_MIRROR | (nchunk == 1 ? GF_BETA0 : GF_ATOMIC));
+            t.c2 = F + c0 + (int64_t)r0 * x.ld;
+            if (ci == 0) B.add_gemm(q, t, false, true);
+            else B.join_gemm(q, t);
+        }
+        // Z_pp -= Y^T Z[below,p]   (split over K, accumulated atomically)
+        const int chunk = 512;
+        bool opened = false;
+        for (int k0 = 0; k0 < mb; k0 += chunk) {
+            GemmTask u = B.task(SP_Y, Y + k0, ldy, sp_z, F + (r0 + k0) + (int64_t)c0 * x.ld, x.ld,
+                                sp_z, F + c0 + (int64_t)c0 * x.ld, x.ld, b, b, std::min(chunk, mb - k0),
+                                GF_NEG | GF_ATOMIC);
+            if (!opened) { B.add_gemm(q, u, true, true, 2); opened = true; }
+            else B.join_gemm(q, u);
+        }
+    }
+}
+
+static inline int env_int(const char *name, int dflt, int lo)
+{
+    const char *e = getenv(name);
+    return e ? std::max(lo, atoi(e)) : dflt;
+}
+
+}  // namespace spde
