@@ -159,6 +159,32 @@ int spde_selinv(spde_plan *p, int which, double *d_Zq, void *stream);
 int spde_selinv_start(spde_plan *p, int which, void *stream);
 int spde_selinv_fetch(spde_plan *p, int which, double *d_Zq, void *stream);
 
+/* ------------------------------------------------------------------ streamed evaluation (meshes beyond HBM) */
+/* Depth-first, statically planned evaluation for meshes whose factor, update matrices and inverse fronts do not
+ * fit in HBM together (256x256x100: 260 GB of L).  Replaces the same reference calls as spde_factorize /
+ * spde_logdet / spde_solve / spde_selinv (sksparse.cholmod.cholesky + Factor.logdet / solve_A,
+ * advection_diffusion2D.py:193-202) in ONE pass over the supernodal tree: supernodes whose subtree holds more than
+ * `top_bytes` of factor are processed front by front and their panels parked in pinned host memory between the
+ * forward (factorise, log-determinant, forward substitution) and the backward (back substitution, Takahashi
+ * selected inverse) pass; the subtrees below are factorised again in the backward pass instead of being stored.
+ * All device memory is one pool whose size is known when the plan is made (spde_ooc_info).
+ * want_backward = 0: forward pass only (log-determinant, L^-1 P b), smaller pool, no host memory.
+ * build = 0: memory plan only (sizes through spde_ooc_info), no schedules -- for choosing top_bytes. */
+typedef struct spde_ooc spde_ooc;
+int spde_ooc_create(spde_plan *p, int64_t top_bytes, int want_backward, int build, spde_ooc **out);
+void spde_ooc_destroy(spde_ooc *o);
+/* info ids: 0 segments, 1 top segments, 2 pool bytes, 3 forward peak bytes, 4 backward peak bytes, 5 pinned host
+ * bytes, 6 scatter entries, 7 largest forward working set bytes, 8 / 9 launches of all factor / selected-inverse
+ * schedules.  info_d ids: 0 flops factorised twice, 1 / 2 device milliseconds of the last forward / backward pass. */
+int64_t spde_ooc_info(const spde_ooc *o, int what);
+double spde_ooc_info_d(const spde_ooc *o, int what);
+/* d_X: k right-hand sides (n x k row-major) solved in place with the mode bits of spde_solve, k = 0: none;
+ * d_Zq: selected inverse on the pattern of Q, or NULL; h_logdet: log det (Q + tau diag(cnt)). */
+int spde_ooc_run(spde_ooc *o, const double *d_Q, const double *d_cnt, double tau, double *d_X, int k, int mode,
+                 double *d_Zq, double *h_logdet, void *stream);
+/* host export of the per-segment schedules and tables (tests, oracle/plan_emulator.py) */
+int spde_ooc_export(spde_ooc *o, int seg, int prog, int k, int what, void *h_out, int64_t *count, int *elem_size);
+
 /* ------------------------------------------------------------------ likelihood / gradient reductions (K8,K9,K11) */
 /* y = Q x for k right-hand sides (x, y row-major n x k): stencil apply, no index arrays. */
 int spde_q_apply(int M, int N, int T, int bc, const double *d_Q, const double *d_X, int k, double *d_Y, void *stream);

@@ -34,9 +34,16 @@ WTW = np.dtype([("w", "i8"), ("dst", "i8"), ("ldd", "i4"), ("b", "i4"), ("space"
 ZENT = np.dtype([("dst", "i8"), ("dst2", "i8"), ("src", "i8"), ("sn", "i4"), ("pad", "i4")], align=True)
 
 
+SCAT = np.dtype([("src", "i8"), ("dst", "i8")], align=True)
+
+
 class Program:
-    def __init__(self, plan, prog, k=0):
-        ex = plan.export
+    def __init__(self, plan, prog, k=0, seg=None):
+        if seg is None:
+            ex = plan.export
+        else:       # schedule of one segment of the streamed evaluator (spde_ooc_export)
+            def ex(prog, what, dtype, k):
+                return plan.export(seg, prog, what, dtype, k)
         self.launches = ex(prog, 0, LAUNCH, k)
         self.gemm = ex(prog, 1, GEMM, k)
         self.tiles = ex(prog, 2, TILE, k)
@@ -271,3 +278,96 @@ class Emulator:
         Zq = np.zeros(self.nslots * self.n)
         self.run(Program(self.plan, 3), Zq=Zq, zent=zent)
         return Zq
+
+
+class OocEmulator(Emulator):
+    """Interpreter of the streamed evaluator (``csrc/ooc.cu``, ``spde_ooc_run``): one pool array aliased by all
+    operand spaces, segments run depth-first in the exported order, panels of top segments parked in a host array
+    between the passes, bottom segments factorised again in the backward pass."""
+
+    def __init__(self, plan, ooc):
+        self.plan, self.ooc = plan, ooc
+        self.n, self.nslots = plan.n, plan.nslots
+        self.perm = plan.perm.astype(np.int64)
+        tab = ooc.export(-1, 0, 0, "i8").reshape(-1, 16)
+        names = ("top", "keep", "root", "parent", "off_L", "l_size", "off_dinv", "dinv_size", "upd", "u_size", "stack_U",
+                 "stack_Z", "scat0", "scat1", "col0", "col1")
+        self.segs = [dict(zip(names, [int(v) for v in row])) for row in tab]
+        self.order = ooc.export(-1, 0, 1, "i4")
+        self.scat = ooc.export(-1, 0, 2, SCAT)
+        self.diagpos = ooc.export(-1, 0, 3, "i8")
+        self.idx = ooc.export(-1, 0, 4, "i4")
+        self.zent = ooc.export(-1, 0, 5, ZENT)
+        self.zent0 = ooc.export(-1, 0, 6, "i8")
+        self.pool_size = ooc.info(2) // 8
+        self.pool = np.full(self.pool_size, np.nan)      # stale memory must never be read as zeros
+        self.host = {}
+        self.sp = [self.pool] * 8
+        self.status = 0
+
+    def _scatter_factor(self, s, g, Qslots, cnt, tau):
+        self.pool[g["off_L"]:g["off_L"] + g["l_size"]] = 0.0
+        e = self.scat[g["scat0"]:g["scat1"]]
+        v = Qslots[e["src"]].copy()
+        if cnt is not None:
+            slot, node = e["src"] // self.n, e["src"] % self.n
+            dm = slot == self.nslots // 2
+            v[dm] += cnt[node[dm]] * tau
+        self.pool[e["dst"]] = v
+        self.run(Program(self.ooc, 0, seg=s))
+
+    def evaluate(self, Qslots, cnt=None, tau=0.0, X=None, mode=15, selinv=True):
+        """``spde_ooc_run``: returns (logdet, X solved, Zq)."""
+        k = 0
+        if X is not None:
+            X = np.asarray(X, dtype=np.float64).reshape(self.n, -1)
+            k = X.shape[1]
+            kp = k + (k & 1)
+            Xp = np.zeros((self.n, kp))
+            Xp[:, :k] = X[self.perm] if mode & 4 else X
+            self.sp = list(self.sp)
+            self.sp[4] = Xp.reshape(-1).copy()
+        fs, bs = k > 0 and bool(mode & 1), k > 0 and bool(mode & 2)
+        backward = bs or selinv
+        ld = {}
+        end = self.pool_size
+        for s in self.order:
+            g = self.segs[s]
+            self._scatter_factor(s, g, Qslots, cnt, tau)
+            ld[s] = 2.0 * np.log(self.pool[self.diagpos[g["col0"]:g["col1"]]]).sum()
+            if fs:
+                self.run(Program(self.ooc, 1, k, seg=s))
+            if backward and g["top"] and not g["keep"]:
+                self.host[s] = self.pool[g["off_dinv"]:end].copy()
+            if g["u_size"]:
+                self.pool[g["stack_U"]:g["stack_U"] + g["u_size"]] = self.pool[g["upd"]:g["upd"] + g["u_size"]].copy()
+            if not (backward and g["keep"]):
+                # nothing above the stack may be relied upon later (except the root kept between the passes)
+                self.pool[g["stack_U"] + g["u_size"]:end] = np.nan
+        Zq = np.zeros(self.nslots * self.n) if selinv else None
+        if backward:
+            for s in self.order[::-1]:
+                g = self.segs[s]
+                if not g["keep"]:
+                    if g["top"]:
+                        self.pool[g["off_dinv"]:end] = self.host.pop(s)
+                    else:
+                        self._scatter_factor(s, g, Qslots, cnt, tau)
+                if bs:
+                    self.run(Program(self.ooc, 2, k, seg=s))
+                if selinv:
+                    z0 = int(self.zent0[s])
+                    z1 = int(self.zent0[s + 1]) if s + 1 < len(self.segs) else len(self.zent)
+                    self.run(Program(self.ooc, 3, seg=s), Zq=Zq, zent=self.zent[z0:z1])
+                kids = [c for c in range(len(self.segs)) if self.segs[c]["parent"] == s]
+                top = max([self.segs[c]["stack_Z"] + self.segs[c]["u_size"] for c in kids], default=max(g["stack_Z"], 0))
+                self.pool[top:end] = np.nan
+        out = None
+        if k:
+            Xp = self.sp[4].reshape(self.n, -1)[:, :k]
+            out = np.empty_like(Xp)
+            if mode & 8:
+                out[self.perm] = Xp
+            else:
+                out[:] = Xp
+        return sum(ld[s] for s in self.order), out, Zq

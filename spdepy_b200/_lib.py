@@ -76,6 +76,12 @@ _SIGS = {
     "spde_fill_kron": (c_int, [c_int, c_int, c_int, c_int, c_vp, c_dbl, c_dbl, c_dbl, c_vp, c_vp]),
     "spde_kron_reduce": (c_int, [c_int, c_int, c_int, c_int, c_vp, c_dbl, c_dbl, c_dbl, c_vp, c_vp]),
     "spde_potrf_bench": (c_int, [c_int, c_int, c_int, c_int, ctypes.POINTER(ctypes.c_float), c_vp, c_vp]),
+    "spde_ooc_create": (c_int, [c_vp, c_i64, c_int, c_int, ctypes.POINTER(c_vp)]),
+    "spde_ooc_destroy": (None, [c_vp]),
+    "spde_ooc_info": (c_i64, [c_vp, c_int]),
+    "spde_ooc_info_d": (c_dbl, [c_vp, c_int]),
+    "spde_ooc_run": (c_int, [c_vp, c_vp, c_vp, c_dbl, c_vp, c_int, c_int, c_vp, ctypes.POINTER(c_dbl), c_vp]),
+    "spde_ooc_export": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_vp, ctypes.POINTER(c_i64), ctypes.POINTER(c_int)]),
 }
 
 EXPORTS = tuple(_SIGS)
@@ -173,6 +179,54 @@ class PlanHandle:
         try:
             if self.h:
                 lib.spde_plan_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+
+class OocHandle:
+    """Owner of one ``spde_ooc*``: the streamed (depth-first, statically planned) evaluator of a plan, for meshes
+    whose factor does not fit in HBM (``include/spde_b200.h``, "streamed evaluation")."""
+
+    def __init__(self, plan: PlanHandle, top_bytes: int, backward: bool = True, build: bool = True):
+        h = c_vp()
+        check(lib.spde_ooc_create(plan.h, int(top_bytes), int(backward), int(build), ctypes.byref(h)))
+        self.h = h
+        self.plan = plan            # keeps the plan alive
+        self.top_bytes, self.backward, self.built = int(top_bytes), bool(backward), bool(build)
+
+    def info(self, what: int) -> int:
+        return int(lib.spde_ooc_info(self.h, what))
+
+    def info_d(self, what: int) -> float:
+        return float(lib.spde_ooc_info_d(self.h, what))
+
+    def stats(self) -> dict:
+        return {"segments": self.info(0), "top_segments": self.info(1), "pool_bytes": self.info(2),
+                "peak_forward_bytes": self.info(3), "peak_backward_bytes": self.info(4), "host_bytes": self.info(5),
+                "max_working_set_bytes": self.info(7), "factor_launches": self.info(8), "selinv_launches": self.info(9),
+                "recompute_flops": self.info_d(0), "top_bytes": self.top_bytes}
+
+    def export(self, seg: int, prog: int, what: int, dtype, k: int = 0) -> np.ndarray:
+        cnt, es = c_i64(), c_int()
+        check(lib.spde_ooc_export(self.h, seg, prog, k, what, None, ctypes.byref(cnt), ctypes.byref(es)))
+        dtype = np.dtype(dtype)
+        if cnt.value and dtype.itemsize != es.value:
+            raise SpdeError("export dtype size %d != %d" % (dtype.itemsize, es.value))
+        out = np.empty(cnt.value, dtype)
+        if cnt.value:
+            check(lib.spde_ooc_export(self.h, seg, prog, k, what, out.ctypes.data, None, None))
+        return out
+
+    def run(self, Q_ptr, cnt_ptr, tau: float, X_ptr, k: int, mode: int, Zq_ptr, stream) -> float:
+        ld = c_dbl()
+        check(lib.spde_ooc_run(self.h, Q_ptr, cnt_ptr, float(tau), X_ptr, int(k), int(mode), Zq_ptr, ctypes.byref(ld), stream))
+        return ld.value
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib.spde_ooc_destroy(self.h)
                 self.h = None
         except Exception:
             pass

@@ -455,7 +455,20 @@ static int issue_program(Plan &p, Program &P, int which, cudaStream_t st, double
 {
     int rc = upload_program(P);
     if (rc) return rc;
-    GemmSpaces sp = spaces_of(p, which);
+    ExecCtx ctx;
+    ctx.sp = spaces_of(p, which);
+    ctx.L = p.d_L[which]; ctx.dinv = p.d_dinv[which]; ctx.status = p.d_status + which;
+    ctx.zent = p.d_zentries; ctx.Zq = d_Zq; ctx.which = which; ctx.lanes = true;
+    return issue_program_ex(p, P, ctx, st);
+}
+
+// Issue the launches of an (uploaded) program against explicit base pointers: the in-core stores of a plan
+// (issue_program) or the memory pool of the streamed evaluator (ooc.cu).
+int issue_program_ex(Plan &p, Program &P, const ExecCtx &ctx, cudaStream_t st)
+{
+    const GemmSpaces &sp = ctx.sp;
+    const int which = ctx.which;
+    double *const d_Zq = ctx.Zq;
     std::vector<cudaEvent_t> ev;
     if (p.prof_on) {
         ev.resize(P.launches.size() + 1);
@@ -467,7 +480,7 @@ static int issue_program(Plan &p, Program &P, int which, cudaStream_t st, double
     if (p.prof_on) g_pdl = 0;          // per-launch events need plain stream order
     struct Restore { int v; ~Restore() { g_pdl = v; } } restore{pdl_saved};
     // two-lane schedules: the bulk lane gets its own stream, ordered against the main lane by LK_SYNC records
-    const bool lanes = p.use_lanes && !p.prof_on;
+    const bool lanes = ctx.lanes && p.use_lanes && !p.prof_on;
     const cudaStream_t main_st = st;
     cudaStream_t bulk_st = st;
     if (lanes) {
@@ -507,7 +520,7 @@ static int issue_program(Plan &p, Program &P, int which, cudaStream_t st, double
             else SPDE_CUDA_CHECK(launch_pdl(k_gemv_grouped<false>, dim3(L.ntiles), dim3(256), 0, st, P.d_gemm + L.task0, P.d_tiles + L.tile0, sp));
             break;
         case LK_POTRF:
-            SPDE_CUDA_CHECK(launch_pdl(k_potrf_t<false>, dim3(L.ntasks), dim3(POTRF_THREADS), 0, st, P.d_potrf + L.task0, p.d_L[which], p.d_dinv[which], p.d_status + which,
+            SPDE_CUDA_CHECK(launch_pdl(k_potrf_t<false>, dim3(L.ntasks), dim3(POTRF_THREADS), 0, st, P.d_potrf + L.task0, ctx.L, ctx.dinv, ctx.status,
                                        (long long *)nullptr));
             break;
         case LK_EXTADD:
@@ -520,12 +533,12 @@ static int issue_program(Plan &p, Program &P, int which, cudaStream_t st, double
             SPDE_CUDA_CHECK(launch_pdl(k_selinv_gather, dim3(L.ntiles), dim3(32, 8), 0, st, P.d_gather + L.task0, P.d_tiles + L.tile0, sp));
             break;
         case LK_WTW:
-            SPDE_CUDA_CHECK(launch_pdl(k_wtw, dim3(L.ntasks), dim3(256), 0, st, P.d_wtw + L.task0, p.d_dinv[which], sp));
+            SPDE_CUDA_CHECK(launch_pdl(k_wtw, dim3(L.ntasks), dim3(256), 0, st, P.d_wtw + L.task0, (const double *)ctx.dinv, sp));
             break;
         case LK_EXTRACT: {
             const long long cnt = L.a1 - L.a0;
             SPDE_CUDA_CHECK(launch_pdl(k_extract, dim3((int)std::min<long long>((cnt + 255) / 256, 148 * 16)), dim3(256), 0, st,
-                                       p.d_zentries, (long long)L.a0, (long long)L.a1, sp.base[L.variant], d_Zq));
+                                       ctx.zent, (long long)L.a0, (long long)L.a1, (const double *)sp.base[L.variant], d_Zq));
             break;
         }
         }
@@ -551,6 +564,32 @@ static int issue_program(Plan &p, Program &P, int which, cudaStream_t st, double
     }
     return SPDE_OK;
 }
+
+// host wrappers used by the streamed evaluator (ooc.cu)
+int launch_logdet(const double *d_L, const long long *d_diagpos, int n, double *d_partial, double *d_out, cudaStream_t st)
+{
+    const int nb = 256;
+    count_launch(2);
+    k_logdet_partial<<<nb, 256, 0, st>>>(d_L, d_diagpos, n, d_partial);
+    k_sum_final<<<1, 1024, 0, st>>>(d_partial, nb, 2.0, d_out);
+    SPDE_LAUNCH_CHECK();
+    return SPDE_OK;
+}
+int launch_perm_in(const double *d_X, const int *d_perm, int n, int k, int kp, int use_perm, double *d_Xp, cudaStream_t st)
+{
+    count_launch();
+    k_perm_in<<<148 * 8, 256, 0, st>>>(d_X, d_perm, n, k, kp, use_perm, d_Xp);
+    SPDE_LAUNCH_CHECK();
+    return SPDE_OK;
+}
+int launch_perm_out(const double *d_Xp, const int *d_perm, int n, int k, int kp, int use_perm, double *d_X, cudaStream_t st)
+{
+    count_launch();
+    k_perm_out<<<148 * 8, 256, 0, st>>>(d_Xp, d_perm, n, k, kp, use_perm, d_X);
+    SPDE_LAUNCH_CHECK();
+    return SPDE_OK;
+}
+void init_exec_env(Plan &p);
 
 static void init_gemm_attributes()
 {
@@ -644,17 +683,20 @@ static int run_program(Plan &p, Program &P, int which, cudaStream_t st, double *
     return defer_join ? SPDE_OK : join_store(p, which, st);
 }
 
-static int ensure_device(Plan &p, int which)
+void init_exec_env(Plan &p)
 {
     init_gemm_attributes();
-    {
-        const char *env = getenv("SPDE_GRAPHS");
-        if (env) p.use_graphs = atoi(env);
-        const char *pdl = getenv("SPDE_PDL");
-        if (pdl) g_pdl = atoi(pdl);
-        const char *ln = getenv("SPDE_LANES");
-        if (ln) p.use_lanes = atoi(ln);
-    }
+    const char *env = getenv("SPDE_GRAPHS");
+    if (env) p.use_graphs = atoi(env);
+    const char *pdl = getenv("SPDE_PDL");
+    if (pdl) g_pdl = atoi(pdl);
+    const char *ln = getenv("SPDE_LANES");
+    if (ln) p.use_lanes = atoi(ln);
+}
+
+static int ensure_device(Plan &p, int which)
+{
+    init_exec_env(p);
     if (!(p.device_ready & 1)) {
         std::vector<int> idx(p.sym.rows);
         idx.insert(idx.end(), p.sym.relidx.begin(), p.sym.relidx.end());

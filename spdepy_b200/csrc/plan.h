@@ -3,6 +3,7 @@
 // Built on the host once per mesh from the Symbolic analysis; executed by plan.cu.
 #pragma once
 #include <map>
+#include <string>
 #include <vector>
 
 #include "gemm.cuh"
@@ -133,5 +134,22 @@ struct Plan {
     Program &solve_program(int k, int dir);
     void build_selinv_program();
 };
+
+// explicit execution context of a program: base pointers of the eight operand spaces, the factor / inverse-block
+// stores the POTRF and W^T W kernels address directly, the status word and the extraction table
+struct ExecCtx {
+    GemmSpaces sp;
+    double *L = nullptr, *dinv = nullptr;
+    int *status = nullptr;
+    const ZEntry *zent = nullptr;
+    double *Zq = nullptr;
+    int which = 0;
+    bool lanes = false;
+};
+int issue_program_ex(Plan &p, Program &P, const ExecCtx &ctx, cudaStream_t st);
+int launch_logdet(const double *d_L, const long long *d_diagpos, int n, double *d_partial, double *d_out, cudaStream_t st);
+int launch_perm_in(const double *d_X, const int *d_perm, int n, int k, int kp, int use_perm, double *d_Xp, cudaStream_t st);
+int launch_perm_out(const double *d_Xp, const int *d_perm, int n, int k, int kp, int use_perm, double *d_X, cudaStream_t st);
+void init_exec_env(Plan &p);
 
 }  // namespace spde
