@@ -9,6 +9,7 @@ only; every numeric step is a kernel of ``libspde_b200.so``.
 from __future__ import annotations
 
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -235,6 +236,66 @@ class Engine:
         Z = torch.empty(self.nslots * self.n, dtype=F64, device=_dev())
         check(lib.spde_selinv(self.plan.h, which, ptr(Z), _stream()))
         return Z
+
+    # ------------------------------------------------------------------ streamed evaluation (csrc/ooc.cu)
+    streamed = None      # None: automatic (in-core stores would not fit the device); True / False: forced
+
+    def incore_bytes(self) -> int:
+        """Device bytes of one factor store with its update-matrix arenas and inverse fronts (the in-core path)."""
+        st = self.plan.stats()
+        return st["factor_bytes"] + st["arena_bytes"] + st["zarena_bytes"]
+
+    def use_streamed(self) -> bool:
+        env = os.environ.get("SPDE_STREAMED")
+        if env is not None:
+            return env not in ("0", "")
+        if self.streamed is not None:
+            return bool(self.streamed)
+        total = torch.cuda.get_device_properties(torch.cuda.current_device()).total_memory
+        return self.incore_bytes() + 3 * 8 * self.nslots * self.n > 0.9 * total
+
+    def ooc(self, backward: bool = True) -> _lib.OocHandle:
+        """The streamed evaluator of this mesh (one at a time: its pool is most of the device).  The threshold that
+        separates front-by-front supernodes (panels parked in pinned host memory) from recomputed subtrees is
+        ``SPDE_OOC_TOP_BYTES`` or, by default, the smallest one whose pool and host pool fit this box."""
+        cur = getattr(self, "_ooc", None)
+        if cur is not None and cur.backward == backward:
+            return cur
+        self._ooc = None
+        del cur
+        torch.cuda.empty_cache()
+        env = os.environ.get("SPDE_OOC_TOP_BYTES")
+        if env is not None:
+            thr = int(float(env))
+        else:
+            import psutil
+            total = torch.cuda.get_device_properties(torch.cuda.current_device()).total_memory
+            dev_budget = total - 4 * 8 * self.nslots * self.n - (6 << 30)
+            host_budget = 0.6 * psutil.virtual_memory().total
+            thr = None
+            for c in [2.0 ** e * 1e9 for e in range(-6, 8)]:
+                st = _lib.OocHandle(self.plan, int(c), backward, False).stats()
+                if st["pool_bytes"] <= dev_budget and st["host_bytes"] <= host_budget:
+                    thr = int(c)
+                    break
+            if thr is None:
+                raise MemoryError("streamed evaluation of the %dx%dx%d mesh fits neither this device nor this host"
+                                  % (self.M, self.N, self.T))
+        self._ooc = _lib.OocHandle(self.plan, thr, backward, True)
+        return self._ooc
+
+    def streamed_eval(self, Q: torch.Tensor, cnt=None, tau: float = 0.0, X=None, mode: int = 15, selinv: bool = True):
+        """One depth-first pass: returns (logdet(Q + tau diag(cnt)), X solved in place or None, Z on the pattern
+        of Q or None).  A backward pass (back substitution, selected inverse) runs when asked for."""
+        k = 0 if X is None else (X.shape[1] if X.dim() > 1 else 1)
+        backward = selinv or (k > 0 and bool(mode & 2))
+        o = self.ooc(backward)
+        Z = torch.empty(self.nslots * self.n, dtype=F64, device=_dev()) if selinv else None
+        if X is not None:
+            assert X.is_cuda and X.dtype == F64 and X.is_contiguous() and X.shape[0] == self.n
+        ld = o.run(ptr(Q), ptr(cnt), tau, ptr(X), k, mode, ptr(Z), _stream())
+        COUNTERS["d2h"] += 8
+        return ld, X, Z
 
     # ------------------------------------------------------------------ reductions (K8, K9, K11)
     def q_apply(self, Q: torch.Tensor, X: torch.Tensor) -> torch.Tensor:

@@ -578,6 +578,11 @@ class SPDE2D:
         # time into 2-D problems, so only the posterior precision needs the 3-D factorisation.  The
         # Hutchinson estimator solves with Q itself and keeps the 3-D factor of the prior.
         collapsed = self.timed and self.collapse_prior and (exact_grad or not grad)
+        if eng.use_streamed():
+            if not collapsed:
+                raise NotImplementedError("meshes beyond device memory (streamed evaluation) need the time-collapsed prior: "
+                                          "a space-time model with exact_grad=True or grad=False")
+            return self._logLike_streamed(par, st, data, obs, cnt, tau, grad)
         if collapsed:
             eng.factorize_async(1, Q, cnt, tau)
             prior = self._prior_collapsed(st, want_grad=grad)
@@ -624,6 +629,42 @@ class SPDE2D:
             W = eng.sddmm(TrQ, Vp, a)
             W = eng.sddmm(TrQc, Vp, -a, W)
             tr_tau = Engine.wdot(TrQc, Vp, cnt) * tau / nh1
+        W = eng.sddmm(mu_c, mu_c, -0.5, W)
+        g_par = np.zeros(par.size)
+        gi = self._grad_from_weights(st, W, prior)
+        g_par[:len(gi)] = gi
+        g_par[-1] = nobs * r / 2 - 1 / 2 * tr_tau * r - tau / 2 * resid
+        return -like / (nobs * r), -g_par / (nobs * r)
+
+
+    def _logLike_streamed(self, par, st, data, obs, cnt, tau, grad):
+        """``logLike`` for meshes whose posterior factor does not fit in HBM (``Engine.streamed_eval``): the prior
+        terms come from the 2-D factorisations of the time-collapsed prior, the posterior precision is factorised
+        depth-first.  Without the gradient only the forward pass runs and the quadratic terms use
+        ``mu^T Q mu + tau |y - S mu|^2 = tau y^T y - b^T Q_c^-1 b = tau y^T y - |L^-1 P b|^2`` (b = tau S^T y);
+        with it, the backward pass returns the conditional mean and the selected inverse as the in-core path."""
+        eng = self.engine
+        r, nobs = self.r, self._obs["nobs"]
+        Q = st["Q"]
+        prior = self._prior_collapsed(st, want_grad=grad)
+        ldQ = prior["logdet"]
+        b = eng.scatter_obs(data, obs, tau)
+        if not grad:
+            ldQc, y, _ = eng.streamed_eval(Q, cnt, tau, X=b, mode=1 | 4, selinv=False)
+            yy = Engine.dot(data, data)
+            half = 0.5 * (tau * yy - Engine.dot(y, y))
+            like = 1 / 2 * ldQ * r + nobs * r * np.log(tau) / 2 - 1 / 2 * ldQc * r - half
+            self.last = {"mu_c": None, "logdetQ": ldQ, "logdetQc": ldQc}
+            return -like / (nobs * r)
+        ldQc, mu_c, W = eng.streamed_eval(Q, cnt, tau, X=b, mode=15, selinv=True)
+        quad = Engine.dot(mu_c, eng.q_apply(Q, mu_c))
+        resid = Engine.residual_ss(data, mu_c, obs)
+        like = 1 / 2 * ldQ * r + nobs * r * np.log(tau) / 2 - 1 / 2 * ldQc * r - 1 / 2 * quad - tau / 2 * resid
+        self.last = {"mu_c": mu_c, "logdetQ": ldQ, "logdetQc": ldQc, "quad": quad, "resid": resid}
+        nd = eng.nslots // 2
+        tr_tau = Engine.dot(cnt, W[nd * eng.n:(nd + 1) * eng.n]) * tau
+        W *= -0.5 * r
+        prior["c"] = 0.5 * r
         W = eng.sddmm(mu_c, mu_c, -0.5, W)
         g_par = np.zeros(par.size)
         gi = self._grad_from_weights(st, W, prior)
