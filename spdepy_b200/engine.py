@@ -273,7 +273,7 @@ class Engine:
             dev_budget = total - 4 * 8 * self.nslots * self.n - (6 << 30)
             host_budget = 0.6 * psutil.virtual_memory().total
             thr = None
-            for c in [2.0 ** e * 1e9 for e in range(-6, 8)]:
+            for c in [2.0 ** e * 1e9 for e in range(0, 8)]:      # >= 1 GB: smaller front-by-front segments do not fill the GPU
                 st = _lib.OocHandle(self.plan, int(c), backward, False).stats()
                 if st["pool_bytes"] <= dev_budget and st["host_bytes"] <= host_budget:
                     thr = int(c)
