@@ -370,4 +370,5 @@ class OocEmulator(Emulator):
                 out[self.perm] = Xp
             else:
                 out[:] = Xp
+        self.last_ld = ld
         return sum(ld[s] for s in self.order), out, Zq

@@ -509,6 +509,7 @@ extern "C" double spde_ooc_info_d(const spde_ooc *oo, int what)
     if (what == 0) return o->recompute_flops;
     if (what == 1) return o->last_ms[0];
     if (what == 2) return o->last_ms[1];
+    if (what >= 16 && what - 16 < (int)o->last_ld.size()) return o->last_ld[what - 16];   // log-determinant share of a segment
     return 0.0;
 }
 
@@ -750,6 +751,7 @@ extern "C" int spde_ooc_run(spde_ooc *oo, const double *d_Q, const double *d_cnt
     for (auto &e : ev) cudaEventDestroy(e);
     double sum = 0.0;
     for (int i : o.order) sum += ld[i];       // fixed order
+    o.last_ld = ld;
     if (h_logdet) *h_logdet = sum;
     if (h) { set_error("matrix is not positive definite (pivot " + std::to_string(h - 1) + " of the permuted matrix)"); return SPDE_ERR_NOT_SPD; }
     return SPDE_OK;

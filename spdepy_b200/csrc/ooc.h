@@ -66,6 +66,7 @@ struct Ooc {
     int *d_idx = nullptr, *d_perm = nullptr, *d_status = nullptr;
     long long *d_diag = nullptr;
     double last_ms[2] = {0, 0};               // device time of the forward / backward pass of the last run
+    std::vector<double> last_ld;              // log-determinant share of every segment in the last run
 
     void segment(int64_t top_bytes);
     void plan_memory(bool backward);

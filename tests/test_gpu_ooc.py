@@ -45,7 +45,8 @@ def test_streamed_vs_dense(shape, thr, k, monkeypatch):
     B = rng.normal(size=(n, k))
     X = to_dev(B.copy())
     Z = torch.empty(eng.nslots * n, dtype=torch.float64, device="cuda")
-    ld = ooc.run(to_dev(flat).data_ptr(), to_dev(cnt).data_ptr(), tau, X.data_ptr(), k, 15, Z.data_ptr(),
+    Qd, cd = to_dev(flat), to_dev(cnt)          # keep the device buffers alive across the call
+    ld = ooc.run(Qd.data_ptr(), cd.data_ptr(), tau, X.data_ptr(), k, 15, Z.data_ptr(),
                  torch.cuda.current_stream().cuda_stream)
     sign, ld0 = np.linalg.slogdet(Ad)
     assert abs(ld - ld0) <= 1e-11 * abs(ld0)
@@ -56,7 +57,7 @@ def test_streamed_vs_dense(shape, thr, k, monkeypatch):
     assert np.abs(full[mask] - Zd[mask]).max() <= 1e-9 * np.abs(Zd).max()
     # a second run on the same handle (pool reuse, stale memory from the previous pass)
     X2 = to_dev(B.copy())
-    ld2 = ooc.run(to_dev(flat).data_ptr(), to_dev(cnt).data_ptr(), tau, X2.data_ptr(), k, 15, Z.data_ptr(),
+    ld2 = ooc.run(Qd.data_ptr(), cd.data_ptr(), tau, X2.data_ptr(), k, 15, Z.data_ptr(),
                   torch.cuda.current_stream().cuda_stream)
     assert abs(ld2 - ld) <= 1e-13 * abs(ld) and relerr(X2.cpu().numpy(), X.cpu().numpy()) <= 1e-12
 
@@ -72,17 +73,19 @@ def test_streamed_forward_only_and_not_spd():
     b = np.random.default_rng(2).normal(size=(n, 2))
     y = to_dev(b.copy())
     st = torch.cuda.current_stream().cuda_stream
-    ld = ooc.run(to_dev(flat).data_ptr(), None, 0.0, y.data_ptr(), 2, 1 | 4, None, st)
+    Qd = to_dev(flat)
+    ld = ooc.run(Qd.data_ptr(), None, 0.0, y.data_ptr(), 2, 1 | 4, None, st)
     Ad = A.toarray()
     assert abs(ld - np.linalg.slogdet(Ad)[1]) <= 1e-11 * abs(ld)
     q = np.einsum("ij,ij->", b, np.linalg.solve(Ad, b))
     assert abs(float((y * y).sum()) - q) <= 1e-10 * abs(q)
     with pytest.raises(ValueError):      # a backward pass on a forward-only plan
-        ooc.run(to_dev(flat).data_ptr(), None, 0.0, y.data_ptr(), 2, 15, None, st)
+        ooc.run(Qd.data_ptr(), None, 0.0, y.data_ptr(), 2, 15, None, st)
     bad = flat.copy()
     bad[(eng.nslots // 2) * n + 7] = -1.0
+    Qbad = to_dev(bad)
     with pytest.raises(_lib.NotPositiveDefiniteError):
-        ooc.run(to_dev(bad).data_ptr(), None, 0.0, None, 0, 0, None, st)
+        ooc.run(Qbad.data_ptr(), None, 0.0, None, 0, 0, None, st)
 
 
 def test_streamed_vs_incore_midsize():
