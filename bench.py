@@ -283,6 +283,7 @@ def run_streamed(args):
     m.initFit(inp["data"], idx=inp["idx"])
     eng = m.engine
     eng.streamed = True
+    m.check_selinv = True
     plan = eng.plan
     stats = plan.stats()
     t_plan = time.time() - t0
@@ -326,6 +327,22 @@ def run_streamed(args):
     res = eng.q_apply(Q, mu) + mu * (m._obs["cnt"] * tau)[:, None] - b
     resid = float(res.abs().max() / b.abs().max())
     del res, b
+    trace_check = m.last.get("selinv_trace_over_n")
+    by_kind = None
+    if args.profile_step:
+        # one more evaluation with per-launch CUDA events (outside the timed region): device time per launch kind
+        plan.profile(True)
+        m.logLike(theta, grad=True, exact_grad=True)
+        torch.cuda.synchronize()
+        pms, pcnt = plan.profile(False)
+        kinds = ["gemm", "potrf", "extend_add", "memset", "gather", "wtw", "extract", "gemv"]
+        by_kind = {"ms": {k: float(pms[i].sum()) for i, k in enumerate(kinds)},
+                   "launches": {k: int(pcnt[i].sum()) for i, k in enumerate(kinds)},
+                   "passes_ms": [ooc.info_d(1), ooc.info_d(2)],
+                   "gemm_tflops": (alg_all := 3.0 * stats["flops"] + ost["recompute_flops"]) / (float(pms[0].sum()) * 1e-3) / 1e12,
+                   "note": "profiled evaluation (events around every launch); gemm_tflops = (3 sum cc^2 + flops factorised twice) / "
+                           "summed k_gemm_grouped time; host<->device panel copies and update-matrix moves are not launches: "
+                           "their time is passes_ms minus the sum over kinds"}
     like_fwd = None
     if args.check_forward:
         like_fwd = float(m.logLike(theta, grad=False))
@@ -358,7 +375,8 @@ def run_streamed(args):
                      "peak_source": "cuBLAS DGEMM 8192^3 measured in this run", "algorithmic_flops_per_step": alg},
         "cpu_baseline": None,
         "checks": {"conditional_mean_residual_inf": resid, "like_full": float(like), "like_forward_only": like_fwd,
-                   "grad_inf_norm": float(np.abs(jac).max())},
+                   "grad_inf_norm": float(np.abs(jac).max()), "selinv_trace_over_n": trace_check},
+        "profile_by_kind": by_kind, "passes_ms_per_step": [list(p) for p in passes],
         "last_like": float(like), "last_jac": [float(v) for v in jac],
     }
     print(json.dumps(line))
@@ -558,6 +576,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--streamed", action="store_true", help="force the streamed (depth-first) evaluator on any workload")
     ap.add_argument("--mesh", type=int, nargs=3, default=None, help="override the mesh of the workload (streamed runs)")
+    ap.add_argument("--profile-step", action="store_true", help="streamed runs: one extra evaluation with per-launch events")
     ap.add_argument("--check-forward", action="store_true", help="streamed runs: also evaluate logLike(grad=False) (forward pass only)")
     args = ap.parse_args()
     if args.impl == "reference":

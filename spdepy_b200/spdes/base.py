@@ -663,6 +663,10 @@ class SPDE2D:
         self.last = {"mu_c": mu_c, "logdetQ": ldQ, "logdetQc": ldQc, "quad": quad, "resid": resid}
         nd = eng.nslots // 2
         tr_tau = Engine.dot(cnt, W[nd * eng.n:(nd + 1) * eng.n]) * tau
+        if getattr(self, "check_selinv", False):
+            # size-independent checksum of the selected inverse: the pattern of Q_c is inside the extracted pattern,
+            # so sum_e (Q_c)_e Z_e = tr(Q_c Q_c^-1) = n exactly
+            self.last["selinv_trace_over_n"] = (Engine.dot(Q, W) + tr_tau) / eng.n
         W *= -0.5 * r
         prior["c"] = 0.5 * r
         W = eng.sddmm(mu_c, mu_c, -0.5, W)

@@ -128,9 +128,11 @@ def test_streamed_loglike_vs_oracle(name, monkeypatch):
     monkeypatch.setenv("SPDE_OOC_TOP_BYTES", "30000")
     eng = m.engine
     eng.streamed = True
+    m.check_selinv = True
     try:
         like, jac = m.logLike(d["par"], grad=True, exact_grad=True)
         assert eng._ooc is not None and eng._ooc.stats()["top_segments"] > 0
+        assert abs(m.last["selinv_trace_over_n"] - 1.0) <= 1e-10      # tr(Q_c Z) = n, the full-size checksum of bench c4
         like_only = m.logLike(d["par"], grad=False)
     finally:
         eng.streamed = None
