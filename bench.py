@@ -343,6 +343,12 @@ def run_streamed(args):
                    "note": "profiled evaluation (events around every launch); gemm_tflops = (3 sum cc^2 + flops factorised twice) / "
                            "summed k_gemm_grouped time; host<->device panel copies and update-matrix moves are not launches: "
                            "their time is passes_ms minus the sum over kinds"}
+    cpu = None
+    if not args.no_cpu:
+        cpu = cpu_reference(name, stats)
+        if name == "c4":
+            cpu["sample"] += ("; at this size the CPU path cannot actually run: its two factors need 2 x 260 GB against %d GB "
+                              "of host RAM, so the scaled figure is a time model, not a measurement" % (os.sysconf("SC_PAGE_SIZE") * os.sysconf("SC_PHYS_PAGES") // 10 ** 9))
     like_fwd = None
     if args.check_forward:
         like_fwd = float(m.logLike(theta, grad=False))
@@ -373,7 +379,7 @@ def run_streamed(args):
                      "note": "whole-pass rate: 3 sum cc^2 / (forward + backward device time), includes scatter, extend-add, "
                              "host transfers and the recomputed subtrees -- a lower bound of the kernel's own rate",
                      "peak_source": "cuBLAS DGEMM 8192^3 measured in this run", "algorithmic_flops_per_step": alg},
-        "cpu_baseline": None,
+        "cpu_baseline": cpu,
         "checks": {"conditional_mean_residual_inf": resid, "like_full": float(like), "like_forward_only": like_fwd,
                    "grad_inf_norm": float(np.abs(jac).max()), "selinv_trace_over_n": trace_check},
         "profile_by_kind": by_kind, "passes_ms_per_step": [list(p) for p in passes],
