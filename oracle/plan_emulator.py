@@ -14,7 +14,7 @@ import numpy as np
 
 GF_LOWER, GF_BETA0, GF_NEG, GF_ATOMIC, GF_GATHER_A, GF_SCATTER_C, GF_MIRROR = (1 << 9, 1 << 10, 1 << 11, 1 << 12,
                                                                             1 << 13, 1 << 14, 1 << 15)
-LK_GEMM, LK_POTRF, LK_EXTADD, LK_ZERO, LK_GATHER, LK_WTW, LK_EXTRACT, LK_GEMV, LK_SYNC = range(9)
+LK_GEMM, LK_POTRF, LK_EXTADD, LK_ZERO, LK_GATHER, LK_WTW, LK_EXTRACT, LK_GEMV, LK_SYNC, LK_COPY = range(10)
 NB = 64
 CFG = {0: (128, 128), 1: (128, 64), 2: (64, 64)}
 
@@ -222,12 +222,17 @@ class Emulator:
                 self._wtw(P, L)
             elif kind == LK_SYNC:
                 continue        # lane ordering: the launch list is a valid serial order
+            elif kind == LK_COPY:
+                self._copy(L)
             elif kind == LK_EXTRACT:
                 e = zent[int(L["a0"]):int(L["a1"])]
                 v = self.sp[int(L["variant"])][e["src"]]
                 Zq[e["dst"]] = v
                 m = e["dst2"] >= 0
                 Zq[e["dst2"][m]] = v[m]
+
+    def _copy(self, L):
+        raise NotImplementedError("LK_COPY only occurs in the schedules of the streamed evaluator")
 
     # ---- entry points mirroring the C ABI -------------------------------------------------------
     def factorize(self, Qslots, cnt=None, tau=0.0):
@@ -302,8 +307,22 @@ class OocEmulator(Emulator):
         self.pool_size = ooc.info(2) // 8
         self.pool = np.full(self.pool_size, np.nan)      # stale memory must never be read as zeros
         self.host = {}
+        self.hostbuf = None      # pinned host pool (slices of the overlapped top segments)
+        self.chunks = None       # slice table of the segment in flight
         self.sp = [self.pool] * 8
         self.status = 0
+
+    def _copy(self, L):
+        """LK_COPY: variant 0 parks pool[a0:a0+a1] at host offset task0 (only when a backward pass follows);
+        variant 1 is the point where slice a0 of the panel must have come back -- the interpreter fetches it exactly
+        there, so a step that reads a slice before its wait record sees the NaN poison."""
+        if int(L["variant"]) == 0:
+            if self.hostbuf is not None:
+                a0, a1, h = int(L["a0"]), int(L["a1"]), int(L["task0"])
+                self.hostbuf[h:h + a1] = self.pool[a0:a0 + a1]
+        else:
+            off, ln, h = (int(v) for v in self.chunks[int(L["a0"])])
+            self.pool[off:off + ln] = self.hostbuf[h:h + ln]
 
     def _scatter_factor(self, s, g, Qslots, cnt, tau):
         self.pool[g["off_L"]:g["off_L"] + g["l_size"]] = 0.0
@@ -331,14 +350,16 @@ class OocEmulator(Emulator):
         backward = bs or selinv
         ld = {}
         end = self.pool_size
+        self.hostbuf = np.full(max(self.ooc.info(5) // 8, 1), np.nan) if backward else None
+        slices = {s: self.ooc.export(s, 0, 7, "i8").reshape(-1, 3) for s in range(len(self.segs))}
         for s in self.order:
             g = self.segs[s]
             self._scatter_factor(s, g, Qslots, cnt, tau)
             ld[s] = 2.0 * np.log(self.pool[self.diagpos[g["col0"]:g["col1"]]]).sum()
             if fs:
                 self.run(Program(self.ooc, 1, k, seg=s))
-            if backward and g["top"] and not g["keep"]:
-                self.host[s] = self.pool[g["off_dinv"]:end].copy()
+            if backward and g["top"] and not g["keep"] and not len(slices[s]):
+                self.host[s] = self.pool[g["off_dinv"]:end].copy()      # (overlapped segments parked their slices already)
             if g["u_size"]:
                 self.pool[g["stack_U"]:g["stack_U"] + g["u_size"]] = self.pool[g["upd"]:g["upd"] + g["u_size"]].copy()
             if not (backward and g["keep"]):
@@ -348,17 +369,29 @@ class OocEmulator(Emulator):
         if backward:
             for s in self.order[::-1]:
                 g = self.segs[s]
+                fetch = False
                 if not g["keep"]:
-                    if g["top"]:
+                    if g["top"] and len(slices[s]):
+                        fetch = True
+                        off, ln, h = (int(v) for v in slices[s][-1])          # inverse diagonal blocks first
+                        self.pool[off:off + ln] = self.hostbuf[h:h + ln]
+                        self.chunks = slices[s][:-1]
+                    elif g["top"]:
                         self.pool[g["off_dinv"]:end] = self.host.pop(s)
                     else:
                         self._scatter_factor(s, g, Qslots, cnt, tau)
-                if bs:
+                if bs and not fetch:
                     self.run(Program(self.ooc, 2, k, seg=s))
                 if selinv:
                     z0 = int(self.zent0[s])
                     z1 = int(self.zent0[s + 1]) if s + 1 < len(self.segs) else len(self.zent)
                     self.run(Program(self.ooc, 3, seg=s), Zq=Zq, zent=self.zent[z0:z1])
+                if fetch:
+                    if not selinv:       # spde_ooc_run waits for the last slice (number 0) before the solve
+                        for off, ln, h in self.chunks:
+                            self.pool[int(off):int(off + ln)] = self.hostbuf[int(h):int(h + ln)]
+                    if bs:
+                        self.run(Program(self.ooc, 2, k, seg=s))
                 kids = [c for c in range(len(self.segs)) if self.segs[c]["parent"] == s]
                 top = max([self.segs[c]["stack_Z"] + self.segs[c]["u_size"] for c in kids], default=max(g["stack_Z"], 0))
                 self.pool[top:end] = np.nan

@@ -305,8 +305,12 @@ void Ooc::build_programs()
     int max_nr = 2;
     for (const SNode &x : osn) max_nr = std::max(max_nr, x.nr);
     ident_base = 2 * (int64_t)S.rows.size();
+    const bool overlap_on = env_int("SPDE_OOC_OVERLAP", 1, 0) != 0;
     for (size_t gi = 0; gi < segs.size(); gi++) {
         OocSeg &g = segs[gi];
+        g.overlap = overlap_on && g.top && g.host_off >= 0;
+        g.chunk_off.clear();
+        g.chunk_len.clear();
         // ---- factorisation: levels bottom-up
         {
             Program &P = g.factor;
@@ -339,7 +343,21 @@ void Ooc::build_programs()
                 LevelBuilder B(P);
                 for (int s : lev) {
                     std::vector<Step> q;
-                    factor_node_steps(B, osn[s], sp_u, OUTER, q);
+                    if (g.overlap) {
+                        // a spilled top segment (one front): every outer block of columns goes to the host as soon
+                        // as it holds its final values, on the copy stream, under the right-looking update that follows
+                        const SNode &x = osn[s];
+                        factor_node_steps(B, x, sp_u, OUTER, q, [&](std::vector<Step> &qq, int P0, int P1) {
+                            const int c0 = P0 * NB, c1 = std::min(P1 * NB, x.nc);
+                            const int64_t off = x.panel + (int64_t)c0 * x.ld, len = (int64_t)(c1 - c0) * x.ld;
+                            g.chunk_off.push_back(off);
+                            g.chunk_len.push_back(len);
+                            qq.push_back(copy_step(0, off, len, g.host_off + (off - g.off_dinv)));
+                        });
+                        q.push_back(copy_step(0, g.off_dinv, g.dinv_size, g.host_off));
+                    } else {
+                        factor_node_steps(B, osn[s], sp_u, OUTER, q);
+                    }
                     B.seq.push_back(std::move(q));
                 }
                 B.flush();
@@ -380,7 +398,16 @@ void Ooc::build_programs()
                 int64_t yoff = g.off_y;
                 for (int s : lev) {
                     std::vector<Step> q;
-                    selinv_node_steps(B, osn[s], sp_z, yoff, splitk_min, kchunk, q);
+                    if (g.overlap) {
+                        // block columns are visited last to first: wait for slice c just before its last block column
+                        const int nblk = osn[s].nblk;
+                        selinv_node_steps(B, osn[s], sp_z, yoff, splitk_min, kchunk, q, [&](std::vector<Step> &qq, int pb) {
+                            const int c = pb / OUTER;
+                            if (pb == std::min((c + 1) * OUTER, nblk) - 1) qq.push_back(copy_step(1, c, 0, 0));
+                        });
+                    } else {
+                        selinv_node_steps(B, osn[s], sp_z, yoff, splitk_min, kchunk, q);
+                    }
                     yoff += (int64_t)osn[s].ld * NB;
                     B.seq.push_back(std::move(q));
                 }
@@ -480,6 +507,8 @@ extern "C" void spde_ooc_destroy(spde_ooc *oo)
     cudaFree(o->d_pool); cudaFree(o->d_Xp); cudaFree(o->d_ld); cudaFree(o->d_red); cudaFree(o->d_stage);
     cudaFree(o->d_idx); cudaFree(o->d_perm); cudaFree(o->d_status); cudaFree(o->d_diag);
     if (o->h_pool) cudaFreeHost(o->h_pool);
+    if (o->copy_stream) { cudaStreamDestroy(o->copy_stream); cudaEventDestroy(o->copy_fork); cudaEventDestroy(o->copy_done); }
+    for (cudaEvent_t e : o->fetch_ev) cudaEventDestroy(e);
     delete o;      // the programs only borrowed slices of the staging buffer
 }
 
@@ -538,6 +567,15 @@ extern "C" int spde_ooc_export(spde_ooc *oo, int seg, int prog, int k, int what,
         case 4: EXP(P->ext) break;
         case 5: EXP(P->gather) break;
         case 6: EXP(P->wtw) break;
+        case 7:     // slices of an overlapped top segment: (pool offset, doubles, host offset), then [dinv] as the last row
+            tab.clear();
+            if (g.overlap) {
+                for (size_t c = 0; c < g.chunk_off.size(); c++) {
+                    tab.push_back(g.chunk_off[c]); tab.push_back(g.chunk_len[c]); tab.push_back(g.host_off + (g.chunk_off[c] - g.off_dinv));
+                }
+                tab.push_back(g.off_dinv); tab.push_back(g.dinv_size); tab.push_back(g.host_off);
+            }
+            EXP(tab) break;
         default: set_error("spde_ooc_export: bad what"); return SPDE_ERR_ARG;
         }
     } else {
@@ -601,6 +639,18 @@ int ensure_ooc_device(Ooc &o, int k, bool backward, size_t stage_need)
         SPDE_CUDA_CHECK(cudaMalloc((void **)&o.d_status, sizeof(int)));
         SPDE_CUDA_CHECK(cudaMalloc((void **)&o.d_ld, std::max<size_t>(o.segs.size(), 1) * sizeof(double)));
         SPDE_CUDA_CHECK(cudaMalloc((void **)&o.d_red, 1024 * sizeof(double)));
+    }
+    if (!o.copy_stream) {
+        SPDE_CUDA_CHECK(cudaStreamCreateWithFlags(&o.copy_stream, cudaStreamNonBlocking));
+        SPDE_CUDA_CHECK(cudaEventCreateWithFlags(&o.copy_fork, cudaEventDisableTiming));
+        SPDE_CUDA_CHECK(cudaEventCreateWithFlags(&o.copy_done, cudaEventDisableTiming));
+    }
+    size_t nev = 1;
+    for (const OocSeg &g : o.segs) nev = std::max(nev, g.chunk_off.size());
+    while (o.fetch_ev.size() < nev) {
+        cudaEvent_t e;
+        SPDE_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        o.fetch_ev.push_back(e);
     }
     if (backward && o.host_size > 0 && !o.h_pool) {
         cudaError_t e = cudaHostAlloc((void **)&o.h_pool, (size_t)o.host_size * sizeof(double), cudaHostAllocDefault);
@@ -672,6 +722,10 @@ extern "C" int spde_ooc_run(spde_ooc *oo, const double *d_Q, const double *d_cnt
     ctx.sp.base[SP_X] = o.d_Xp;
     ctx.sp.idx = o.d_idx;
     ctx.L = o.d_pool; ctx.dinv = o.d_pool; ctx.status = o.d_status; ctx.Zq = d_Zq; ctx.which = 0; ctx.lanes = false;
+    // LK_COPY records of the overlapped top segments: no host pool = no backward pass = nothing is parked
+    ctx.h_pool = backward ? o.h_pool : nullptr;
+    ctx.copy_stream = o.copy_stream; ctx.copy_fork = o.copy_fork; ctx.fetch_ev = &o.fetch_ev;
+    const cudaStream_t cs = p.prof_on ? st : o.copy_stream;     // profiled evaluations keep everything on one stream
     cudaEvent_t ev[3];
     for (auto &e : ev) SPDE_CUDA_CHECK(cudaEventCreate(&e));
     SPDE_CUDA_CHECK(cudaMemsetAsync(o.d_status, 0, sizeof(int), st));
@@ -703,9 +757,16 @@ extern "C" int spde_ooc_run(spde_ooc *oo, const double *d_Q, const double *d_cnt
             if ((rc = sg.program(F))) return rc;
             if ((rc = issue_program_ex(p, F, ctx, st))) return rc;
         }
-        if (backward && g.host_off >= 0)
-            SPDE_CUDA_CHECK(cudaMemcpyAsync(o.h_pool + g.host_off, o.d_pool + g.off_dinv, (size_t)(o.pool_size - g.off_dinv) * sizeof(double),
-                                            cudaMemcpyDeviceToHost, st));
+        if (backward && g.host_off >= 0) {
+            if (g.overlap) {
+                // the slices left on the copy stream during the factorisation; the next segment reuses this memory
+                SPDE_CUDA_CHECK(cudaEventRecord(o.copy_done, o.copy_stream));
+                SPDE_CUDA_CHECK(cudaStreamWaitEvent(st, o.copy_done, 0));
+            } else {
+                SPDE_CUDA_CHECK(cudaMemcpyAsync(o.h_pool + g.host_off, o.d_pool + g.off_dinv, (size_t)(o.pool_size - g.off_dinv) * sizeof(double),
+                                                cudaMemcpyDeviceToHost, st));
+            }
+        }
         if (g.u_size > 0)
             SPDE_CUDA_CHECK(cudaMemcpyAsync(o.d_pool + g.stack_U, o.d_pool + o.osn[g.root].upd, (size_t)g.u_size * sizeof(double),
                                             cudaMemcpyDeviceToDevice, st));
@@ -717,17 +778,35 @@ extern "C" int spde_ooc_run(spde_ooc *oo, const double *d_Q, const double *d_cnt
         for (int q = (int)o.order.size() - 1; q >= 0; q--) {
             OocSeg &g = o.segs[o.order[q]];
             Stage sg{o.d_stage, (size_t)o.stage_bytes, 0, st};
+            const bool fetch = !g.keep && g.top && g.overlap;
             if (!g.keep) {
-                if (g.top) {
+                if (fetch) {
+                    // the panel comes back slice by slice, last slice first (the order the Takahashi recursion walks
+                    // the block columns), behind everything that still uses this memory
+                    SPDE_CUDA_CHECK(cudaEventRecord(o.copy_fork, st));
+                    SPDE_CUDA_CHECK(cudaStreamWaitEvent(cs, o.copy_fork, 0));
+                    SPDE_CUDA_CHECK(cudaMemcpyAsync(o.d_pool + g.off_dinv, o.h_pool + g.host_off, (size_t)g.dinv_size * sizeof(double),
+                                                    cudaMemcpyHostToDevice, cs));
+                    for (int c = (int)g.chunk_off.size() - 1; c >= 0; c--) {
+                        SPDE_CUDA_CHECK(cudaMemcpyAsync(o.d_pool + g.chunk_off[c], o.h_pool + g.host_off + (g.chunk_off[c] - g.off_dinv),
+                                                        (size_t)g.chunk_len[c] * sizeof(double), cudaMemcpyHostToDevice, cs));
+                        SPDE_CUDA_CHECK(cudaEventRecord(o.fetch_ev[c], cs));
+                    }
+                } else if (g.top) {
                     SPDE_CUDA_CHECK(cudaMemcpyAsync(o.d_pool + g.off_dinv, o.h_pool + g.host_off, (size_t)(o.pool_size - g.off_dinv) * sizeof(double),
                                                     cudaMemcpyHostToDevice, st));
                 } else if ((rc = scatter_and_factor(g, sg))) return rc;
             }
-            if (bsolve) {
+            auto back_substitution = [&]() -> int {
+                if (!bsolve) return SPDE_OK;
                 Program &B = o.solve_program(g, k, 1);
-                if ((rc = sg.program(B))) return rc;
-                if ((rc = issue_program_ex(p, B, ctx, st))) return rc;
-            }
+                int r = sg.program(B);
+                if (r) return r;
+                return issue_program_ex(p, B, ctx, st);
+            };
+            // the solve and the recursion only read the factor, so their order is free: with the panel still arriving
+            // the recursion goes first (it waits slice by slice) and the solve runs once everything is there
+            if (!fetch && (rc = back_substitution())) return rc;
             if (d_Zq) {
                 ZEntry *d_ze = nullptr;
                 if ((rc = sg.put(o.zent.data() + g.zent0, (size_t)(g.zent1 - g.zent0), &d_ze))) return rc;
@@ -735,6 +814,10 @@ extern "C" int spde_ooc_run(spde_ooc *oo, const double *d_Q, const double *d_cnt
                 ExecCtx c2 = ctx;
                 c2.zent = d_ze;
                 if ((rc = issue_program_ex(p, g.selinv, c2, st))) return rc;
+            }
+            if (fetch) {
+                SPDE_CUDA_CHECK(cudaStreamWaitEvent(st, o.fetch_ev[0], 0));
+                if ((rc = back_substitution())) return rc;
             }
         }
     }

@@ -12,7 +12,8 @@
 // Every address is known when the plan is built, so a segment's schedule is an ordinary Program with absolute
 // pool offsets and all eight operand spaces (except X) alias the pool.
 // Forward pass (factorise): scatter Q, factor, log-determinant share, forward substitution; the panels of a top
-// segment are then spilled to pinned host memory (only if a backward pass follows), those of a bottom segment are
+// segment are then spilled to pinned host memory (only if a backward pass follows; slice by slice on a copy stream
+// while the factorisation of the same front goes on, LK_COPY records in its schedule), those of a bottom segment are
 // dropped.  Backward pass (back substitution + Takahashi selected inverse), segments in exactly the reverse order:
 // a top segment's panels come back from the host, a bottom segment is factorised again (its subtree does not
 // depend on anything above it).  The last forward segment (the root) stays on the device between the passes.
@@ -37,6 +38,11 @@ struct OocSeg {
     int64_t off_L = 0, off_dinv = 0, off_ar[2] = {0, 0}, off_z[2] = {0, 0}, off_y = 0;
     int64_t stack_U = -1, stack_Z = -1;
     int64_t host_off = -1;                    // [dinv | L] in the pinned host pool, -1: not spilled
+    // overlapped panel traffic of a spilled top segment: the panel in slices of one outer block of columns
+    // (pool offset, doubles); slice c goes to the host as soon as the factorisation has finished its columns and
+    // comes back, last slice first, while the Takahashi recursion already works on the slices behind it
+    int overlap = 0;
+    std::vector<int64_t> chunk_off, chunk_len;
     int keep = 0;                             // factor stays on the device between the passes
     int64_t scat0 = 0, scat1 = 0, zent0 = 0, zent1 = 0;
     int col0 = 0, col1 = 0;                   // column range (new ordering)
@@ -62,6 +68,9 @@ struct Ooc {
     // device state
     double *d_pool = nullptr, *h_pool = nullptr, *d_Xp = nullptr, *d_ld = nullptr, *d_red = nullptr;
     int64_t xp_cap = 0;
+    cudaStream_t copy_stream = nullptr;       // panel traffic of the overlapped top segments
+    cudaEvent_t copy_fork = nullptr, copy_done = nullptr;
+    std::vector<cudaEvent_t> fetch_ev;        // slice c of the segment in flight has come back from the host
     char *d_stage = nullptr;
     int *d_idx = nullptr, *d_perm = nullptr, *d_status = nullptr;
     long long *d_diag = nullptr;

@@ -510,6 +510,23 @@ int issue_program_ex(Plan &p, Program &P, const ExecCtx &ctx, cudaStream_t st)
             if (p.prof_on) cudaEventRecord(ev[++li], st);
             continue;
         }
+        if (L.kind == LK_COPY) {
+            if (L.variant == 0 && !ctx.h_pool) {
+                // forward-only run: nothing is parked
+            } else if (L.variant == 0) {
+                // park a finished slice of the panel in pinned host memory while the factorisation goes on
+                const cudaStream_t cs = p.prof_on ? main_st : ctx.copy_stream;
+                if (cs != main_st) {
+                    SPDE_CUDA_CHECK(cudaEventRecord(ctx.copy_fork, main_st));
+                    SPDE_CUDA_CHECK(cudaStreamWaitEvent(cs, ctx.copy_fork, 0));
+                }
+                SPDE_CUDA_CHECK(cudaMemcpyAsync(ctx.h_pool + L.task0, sp.base[0] + L.a0, (size_t)L.a1 * sizeof(double), cudaMemcpyDeviceToHost, cs));
+            } else {
+                SPDE_CUDA_CHECK(cudaStreamWaitEvent(main_st, (*ctx.fetch_ev)[L.a0], 0));
+            }
+            if (p.prof_on) cudaEventRecord(ev[++li], main_st);
+            continue;
+        }
         st = (lanes && L.lane == 1) ? bulk_st : main_st;
         switch (L.kind) {
         case LK_GEMM:
@@ -555,7 +572,7 @@ int issue_program_ex(Plan &p, Program &P, const ExecCtx &ctx, cudaStream_t st)
             cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
             P.last_ms[i] = ms;
             const Launch &L = P.launches[i];
-            if (L.kind == LK_SYNC) continue;
+            if (L.kind == LK_SYNC || L.kind == LK_COPY) continue;
             const int v = L.kind == LK_GEMM ? L.variant : 0;
             p.prof_ms[L.kind][v] += ms;
             p.prof_cnt[L.kind][v] += 1;
@@ -664,7 +681,7 @@ static int run_program(Plan &p, Program &P, int which, cudaStream_t st, double *
         P.graph_key[which] = key;
     }
     int nk = 0;
-    for (const Launch &L : P.launches) nk += (L.kind != LK_ZERO && L.kind != LK_SYNC);
+    for (const Launch &L : P.launches) nk += (L.kind != LK_ZERO && L.kind != LK_SYNC && L.kind != LK_COPY);
     count_launch(nk);
     if (lane == 1) {
         SPDE_CUDA_CHECK(cudaEventRecord(p.sev_in[which], st));

@@ -40,10 +40,12 @@ struct GatherTask {   // selected inverse: child's trailing block <- parent's fr
 };
 struct WtwTask { long long w; long long dst; int ldd, b, space, pad; };
 
-enum LaunchKind : int { LK_GEMM = 0, LK_POTRF, LK_EXTADD, LK_ZERO, LK_GATHER, LK_WTW, LK_EXTRACT, LK_GEMV, LK_SYNC };
+enum LaunchKind : int { LK_GEMM = 0, LK_POTRF, LK_EXTADD, LK_ZERO, LK_GATHER, LK_WTW, LK_EXTRACT, LK_GEMV, LK_SYNC, LK_COPY };
 // LK_SYNC (two-lane schedules): variant 0 = the bulk lane waits for everything issued so far on the main lane,
 // 1 = record bulk-lane event a0, 2 = the main lane waits for bulk-lane event a0.  The launch list is always a valid
 // serial order, so an executor may ignore the lanes (profiling mode, the NumPy interpreter).
+// LK_COPY (streamed evaluator only): variant 0 = park a0..a0+a1 doubles of the pool at host offset task0 (on the copy
+// stream, after everything issued so far); variant 1 = wait until chunk a0 of the segment's panel has come back from the host.
 
 struct Launch {
     int kind, variant;
@@ -145,6 +147,11 @@ struct ExecCtx {
     double *Zq = nullptr;
     int which = 0;
     bool lanes = false;
+    // streamed evaluator: host pool, copy stream and events of the panel traffic (LK_COPY)
+    double *h_pool = nullptr;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t copy_fork = nullptr;
+    const std::vector<cudaEvent_t> *fetch_ev = nullptr;
 };
 int issue_program_ex(Plan &p, Program &P, const ExecCtx &ctx, cudaStream_t st);
 int launch_logdet(const double *d_L, const long long *d_diagpos, int n, double *d_partial, double *d_out, cudaStream_t st);

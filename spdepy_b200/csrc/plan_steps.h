@@ -36,6 +36,7 @@ struct Step {
     int g0, gn;          // range in the level's GEMM pool
     PotrfTask p;
     WtwTask w;
+    Launch raw;          // LK_COPY: the launch record itself
 };
 
 struct LevelBuilder {
@@ -202,6 +203,8 @@ struct LevelBuilder {
                 for (const Step *st : chosen) prog.potrf.push_back(st->p);
                 L.ntasks = (int)chosen.size();
                 prog.launches.push_back(L);
+            } else if (best.first == LK_COPY) {
+                for (const Step *st : chosen) prog.launches.push_back(st->raw);
             } else if (best.first == LK_WTW) {
                 Launch L;
                 memset(&L, 0, sizeof L);
@@ -274,7 +277,9 @@ static inline void push_gather_task(Program &P, Launch &L, long long dst, int ld
 // Dense partial Cholesky of one front (panel already assembled): left-looking GEMM inside an outer block of
 // `outer` 64-column blocks, 64x64 POTRF with explicit inverse, TRSM-as-GEMM with that inverse, right-looking GEMM
 // beyond the outer block, one SYRK of the update matrix with K = all pivot columns.
-static inline void factor_node_steps(LevelBuilder &B, const SNode &x, int sp_u, int outer, std::vector<Step> &q)
+// `after_outer(q, P0, P1)` (optional) is called when the block columns P0..P1-1 hold their final values.
+template <class Hook>
+static inline void factor_node_steps(LevelBuilder &B, const SNode &x, int sp_u, int outer, std::vector<Step> &q, Hook after_outer)
 {
     const int mrows = x.ncp + x.nr;     // panel rows in use (the gap row of an odd nc is zero)
     for (int P0 = 0; P0 < x.nblk; P0 += outer) {
@@ -304,6 +309,7 @@ static inline void factor_node_steps(LevelBuilder &B, const SNode &x, int sp_u, 
                                  SP_L, x.panel + r0 + (int64_t)c0 * x.ld, x.ld,
                                  mrows - r0, b, b, GF_BETA0), false, false);
         }
+        after_outer(q, P0, P1);
         if (P1 < x.nblk) {
             // right-looking update of the panel columns beyond this outer block
             const int cR = P1 * NB, K = cR - cP;
@@ -318,6 +324,20 @@ static inline void factor_node_steps(LevelBuilder &B, const SNode &x, int sp_u, 
         B.add_gemm(q, B.task(SP_L, x.panel + x.ncp, x.ld, SP_L, x.panel + x.ncp, x.ld,
                              sp_u, x.upd, x.ldu, x.nr, x.nr, x.nc, GF_NEG | GF_LOWER), false, false);
     }
+}
+
+static inline void factor_node_steps(LevelBuilder &B, const SNode &x, int sp_u, int outer, std::vector<Step> &q)
+{
+    factor_node_steps(B, x, sp_u, outer, q, [](std::vector<Step> &, int, int) {});
+}
+
+static inline Step copy_step(int variant, int64_t a0, int64_t a1, int64_t host_off)
+{
+    Step st;
+    memset(&st, 0, sizeof st);
+    st.kind = LK_COPY;
+    st.raw.kind = LK_COPY; st.raw.variant = variant; st.raw.a0 = a0; st.raw.a1 = a1; st.raw.task0 = host_off;
+    return st;
 }
 
 // Forward substitution L y = b on the columns of one supernode (X is kp x n, k-major, permuted order).
@@ -398,12 +418,15 @@ static inline void bsolve_node_steps(LevelBuilder &B, const SNode &x, int k, int
 
 // Takahashi recursion on one front whose trailing block Z[below,below] is in place: block columns from last to
 // first.  Y = scratch of ld x 64 doubles at offset Y of the Y space.
+// `before_block(q, p)` (optional) is called before the first step that reads block column p of the factor.
+template <class Hook>
 static inline void selinv_node_steps(LevelBuilder &B, const SNode &x, int sp_z, int64_t Y, int splitk_min, int kchunk,
-                                     std::vector<Step> &q)
+                                     std::vector<Step> &q, Hook before_block)
 {
     const int mrows = x.ncp + x.nr;
     const int64_t F = x.front;
     for (int p = x.nblk - 1; p >= 0; p--) {
+        before_block(q, p);
         const int c0 = p * NB, b = std::min(NB, x.nc - c0);
         const int r0 = (p == x.nblk - 1) ? x.ncp : c0 + NB;
         const int mb = mrows - r0;
@@ -452,6 +475,12 @@ static inline void selinv_node_steps(LevelBuilder &B, const SNode &x, int sp_z, 
             else B.join_gemm(q, u);
         }
     }
+}
+
+static inline void selinv_node_steps(LevelBuilder &B, const SNode &x, int sp_z, int64_t Y, int splitk_min, int kchunk,
+                                     std::vector<Step> &q)
+{
+    selinv_node_steps(B, x, sp_z, Y, splitk_min, kchunk, q, [](std::vector<Step> &, int) {});
 }
 
 static inline int env_int(const char *name, int dflt, int lo)

@@ -140,3 +140,54 @@ def test_streamed_loglike_vs_oracle(name, monkeypatch):
     assert abs(like - like_o) <= 1e-9 * abs(like_o)
     assert np.abs(jac - jac_o).max() <= 1e-9 * np.abs(jac_o).max()
     assert abs(like_only - like_o) <= 1e-9 * abs(like_o)
+
+
+@pytest.mark.parametrize("outer", [1, 2])
+def test_streamed_panel_slices_overlapped(outer, monkeypatch):
+    """Panel traffic of the spilled top segments on the copy stream (LK_COPY records): one 64-column block per outer
+    block makes the fronts on top travel in several slices.  Against dense LAPACK; solve without the selected inverse
+    (the solve waits for the last slice); a profiled run (everything on one stream); and to rounding of the atomics against the same
+    plan with the overlap switched off (SPDE_OOC_OVERLAP=0: whole-panel copies on the compute stream)."""
+    from spdepy_b200 import _lib
+    from spdepy_b200.engine import to_dev
+    eng = _eng(24, 22, 9, 3)
+    n = eng.n
+    A, flat = _spd_on_pattern(eng, 21)
+    Ad = A.toarray()
+    monkeypatch.setenv("SPDE_FACTOR_OUTER", str(outer))
+    ooc = _lib.OocHandle(eng.plan, 150000, True, True)
+    nsl = [max(len(ooc.export(s, 0, 7, "i8")) // 3 - 1, 0) for s in range(ooc.stats()["segments"])]
+    assert max(nsl) >= 4 // outer
+    monkeypatch.setenv("SPDE_OOC_OVERLAP", "0")
+    plain = _lib.OocHandle(eng.plan, 150000, True, True)
+    assert max(len(plain.export(s, 0, 7, "i8")) for s in range(plain.stats()["segments"])) == 0
+    B = np.random.default_rng(4).normal(size=(n, 3))
+    Qd = to_dev(flat)
+    st = torch.cuda.current_stream().cuda_stream
+    out = {}
+    for name, h in (("overlap", ooc), ("plain", plain)):
+        X = to_dev(B.copy())
+        Z = torch.empty(eng.nslots * n, dtype=torch.float64, device="cuda")
+        ld = h.run(Qd.data_ptr(), None, 0.0, X.data_ptr(), 3, 15, Z.data_ptr(), st)
+        out[name] = (ld, X.cpu().numpy(), Z.cpu().numpy())
+    ld, X, Z = out["overlap"]
+    assert abs(ld - np.linalg.slogdet(Ad)[1]) <= 1e-11 * abs(ld)
+    assert relerr(X, np.linalg.solve(Ad, B)) <= 1e-9
+    Zd = np.linalg.inv(Ad)
+    full = eng.pattern.to_csc(Z).toarray()
+    mask = eng.pattern.to_csc(np.ones(eng.nslots * n)).toarray() != 0
+    assert np.abs(full[mask] - Zd[mask]).max() <= 1e-9 * np.abs(Zd).max()
+    assert abs(ld - out["plain"][0]) <= 1e-13 * abs(ld) and relerr(X, out["plain"][1]) <= 1e-12 and relerr(Z, out["plain"][2]) <= 1e-12
+    # solve only (no selected inverse), second run on the same handle
+    X2 = to_dev(B.copy())
+    ld2 = ooc.run(Qd.data_ptr(), None, 0.0, X2.data_ptr(), 3, 15, None, st)
+    assert abs(ld2 - ld) <= 1e-13 * abs(ld) and relerr(X2.cpu().numpy(), X) <= 1e-12
+    # profiled run: copies stay on the compute stream
+    eng.plan.profile(True)
+    try:
+        X3 = to_dev(B.copy())
+        Z3 = torch.empty(eng.nslots * n, dtype=torch.float64, device="cuda")
+        ld3 = ooc.run(Qd.data_ptr(), None, 0.0, X3.data_ptr(), 3, 15, Z3.data_ptr(), st)
+    finally:
+        eng.plan.profile(False)
+    assert abs(ld3 - ld) <= 1e-13 * abs(ld) and relerr(X3.cpu().numpy(), X) <= 1e-12 and relerr(Z3.cpu().numpy(), Z) <= 1e-12

@@ -119,3 +119,67 @@ def test_memory_plan_of_the_headline_mesh_is_monotone():
             assert st["pool_bytes"] <= prev["pool_bytes"] and st["host_bytes"] >= prev["host_bytes"]
             assert st["recompute_flops"] <= prev["recompute_flops"] or prev["segments"] == 1
         prev = st
+
+
+def _dense_case(M, N, T, bc, seed=1):
+    plan = _lib.PlanHandle(M, N, T, bc)
+    pat = Pattern(M, N, T, bc)
+    n = plan.n
+    rng = np.random.default_rng(seed)
+    W = pat.to_csc(rng.normal(size=pat.nslots * n))
+    A = (W + W.T) * 0.5
+    A = sparse.csc_matrix(A + sparse.diags(np.abs(A).sum(axis=1).A1 + 1.0))
+    return plan, pat, A, rng
+
+
+@pytest.mark.parametrize("outer,overlap,selinv", [(1, 1, True), (1, 1, False), (2, 1, True), (1, 0, True)])
+def test_streamed_panel_slices(monkeypatch, outer, overlap, selinv):
+    """Overlapped panel traffic of the spilled top segments (LK_COPY records): with one 64-column block per outer block
+    the fronts on top are parked in several slices during their factorisation and fetched back slice by slice, last
+    slice first, by the wait records inside the Takahashi schedule; the interpreter fetches a slice only at its wait
+    record and everything else above the stack is NaN, so a block column read too early poisons the result.  Also
+    without the selected inverse (the solve waits for all slices) and with the overlap switched off."""
+    monkeypatch.setenv("SPDE_FACTOR_OUTER", str(outer))
+    monkeypatch.setenv("SPDE_OOC_OVERLAP", str(overlap))
+    plan, pat, A, rng = _dense_case(24, 22, 9, 3)
+    n = plan.n
+    ooc = _lib.OocHandle(plan, 150000)
+    st = ooc.stats()
+    nsl = [max(len(ooc.export(s, 0, 7, "i8")) // 3 - 1, 0) for s in range(st["segments"])]
+    if overlap:
+        assert max(nsl) >= 4 // outer and sum(1 for v in nsl if v) == st["top_segments"] - 1   # all but the kept root
+        for s in range(st["segments"]):
+            if nsl[s]:
+                park = ooc.export(s, 0, 0, pe.LAUNCH)
+                wait = ooc.export(s, 3, 0, pe.LAUNCH)
+                assert (park["kind"] == pe.LK_COPY).sum() == nsl[s] + 1          # slices + inverse diagonal blocks
+                assert ((wait["kind"] == pe.LK_COPY) & (wait["variant"] == 1)).sum() == nsl[s]
+    else:
+        assert max(nsl) == 0
+    em = pe.OocEmulator(plan, ooc)
+    B = rng.normal(size=(n, 2))
+    ld, X, Zq = em.evaluate(pat.from_sparse(A), None, 0.0, B, 15, selinv)
+    Ad = A.toarray()
+    sign, ld0 = np.linalg.slogdet(Ad)
+    assert abs(ld - ld0) < 1e-11 * abs(ld0)
+    assert np.abs(Ad @ X - B).max() < 1e-10 * np.abs(B).max()
+    if selinv:
+        Zd = np.linalg.inv(Ad)
+        full = pat.to_csc(Zq).toarray()
+        mask = pat.to_csc(np.ones(pat.nslots * n)).toarray() != 0
+        assert np.abs(full[mask] - Zd[mask]).max() < 1e-10 * np.abs(Zd).max()
+
+
+def test_streamed_forward_only_ignores_park_records(monkeypatch):
+    """A plan built with a backward pass, run forward only: the park records in the factor schedules are skipped."""
+    monkeypatch.setenv("SPDE_FACTOR_OUTER", "1")
+    plan, pat, A, rng = _dense_case(21, 20, 6, 2, seed=5)
+    ooc = _lib.OocHandle(plan, 100000)
+    em = pe.OocEmulator(plan, ooc)
+    b = rng.normal(size=(plan.n, 1))
+    ld, y, _ = em.evaluate(pat.from_sparse(A), None, 0.0, b, 1 | 4, False)
+    assert em.hostbuf is None
+    Ad = A.toarray()
+    assert abs(ld - np.linalg.slogdet(Ad)[1]) < 1e-11 * abs(ld)
+    q = float(b[:, 0] @ np.linalg.solve(Ad, b[:, 0]))
+    assert abs((y * y).sum() - q) < 1e-11 * abs(q)
