@@ -187,13 +187,23 @@ class Model:
             return z.var(axis=1)
         if self._Qdev is None:
             self.setModel()
-        if self.useCov:
-            raise NotImplementedError("qinv(simple=False) with regression columns: use simple=True (sampled variances)")
         eng = self.mod.engine
         eng.factorize(0, self._Qdev)
         Z = eng.selinv(0)
         nd = eng.nslots // 2
-        self.mvar = Z[nd * eng.n:(nd + 1) * eng.n].cpu().numpy()
+        mvar = Z[nd * eng.n:(nd + 1) * eng.n]
+        if self.useCov:
+            # Marginal variances of the bordered latent vector [x; beta] (the reference feeds ``S Q S^T`` with the
+            # shape of Q to R/INLA here, ``model.py:108-116``, which is not a precision matrix; this is the inverse of
+            # the precision the rest of the facade uses): with W = Q11^-1 B and the Schur complement
+            # Sc = C - B^T W,  diag(Z11) = diag(Q11^-1) + rowsum((W Sc^-1) * W),  Z22 = Sc^-1.
+            bd = self._border
+            W = eng.solve(0, bd.B.clone())
+            Sci = np.linalg.inv(bd.C - (bd.B.T @ W).cpu().numpy())
+            mvar = mvar + ((W @ to_dev(Sci)) * W).sum(dim=1)
+            self.mvar = np.concatenate([mvar.cpu().numpy(), np.diag(Sci)])
+            return self.mvar
+        self.mvar = mvar.cpu().numpy()
         return self.mvar
 
 

@@ -192,6 +192,9 @@ def test_bordered_model_with_regression_columns(name, two):
     x[perm] = np.linalg.solve(L.T, z)
     ref = S.toarray() @ (x + mod.mu[:, None])
     assert relerr(X, ref) < 1e-9
+    # marginal variances of [x; beta]: selected inverse of the sparse block + Schur complement of the border
+    mvar = mod.qinv(simple=False)
+    assert mvar.shape == (n + k,) and relerr(mvar, np.diag(np.linalg.inv(Qd))) < 1e-9
 
 
 EDGE_CASES = [
