@@ -168,6 +168,10 @@ int spde_selinv_fetch(spde_plan *p, int which, double *d_Zq, void *stream);
  * forward (factorise, log-determinant, forward substitution) and the backward (back substitution, Takahashi
  * selected inverse) pass; the subtrees below are factorised again in the backward pass instead of being stored.
  * All device memory is one pool whose size is known when the plan is made (spde_ooc_info).
+ * The panel of a front-by-front supernode travels in slices of one outer block of columns on a copy stream of the
+ * evaluator's own: to the host while the factorisation of the same front goes on, and back, last slice first, while
+ * the Takahashi recursion already works on the slices behind it (environment SPDE_OOC_OVERLAP=0 when the schedules
+ * are built: whole-panel copies on the caller's stream instead).
  * want_backward = 0: forward pass only (log-determinant, L^-1 P b), smaller pool, no host memory.
  * build = 0: memory plan only (sizes through spde_ooc_info), no schedules -- for choosing top_bytes. */
 typedef struct spde_ooc spde_ooc;
@@ -182,7 +186,8 @@ double spde_ooc_info_d(const spde_ooc *o, int what);
  * d_Zq: selected inverse on the pattern of Q, or NULL; h_logdet: log det (Q + tau diag(cnt)). */
 int spde_ooc_run(spde_ooc *o, const double *d_Q, const double *d_cnt, double tau, double *d_X, int k, int mode,
                  double *d_Zq, double *h_logdet, void *stream);
-/* host export of the per-segment schedules and tables (tests, oracle/plan_emulator.py) */
+/* host export of the per-segment schedules and tables (tests, oracle/plan_emulator.py); seg >= 0, what = 7: the
+ * slices of an overlapped segment as (pool offset, doubles, host offset) triples, inverse diagonal blocks last */
 int spde_ooc_export(spde_ooc *o, int seg, int prog, int k, int what, void *h_out, int64_t *count, int *elem_size);
 
 /* ------------------------------------------------------------------ likelihood / gradient reductions (K8,K9,K11) */

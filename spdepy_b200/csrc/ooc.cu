@@ -779,45 +779,53 @@ extern "C" int spde_ooc_run(spde_ooc *oo, const double *d_Q, const double *d_cnt
             OocSeg &g = o.segs[o.order[q]];
             Stage sg{o.d_stage, (size_t)o.stage_bytes, 0, st};
             const bool fetch = !g.keep && g.top && g.overlap;
-            if (!g.keep) {
-                if (fetch) {
-                    // the panel comes back slice by slice, last slice first (the order the Takahashi recursion walks
-                    // the block columns), behind everything that still uses this memory
-                    SPDE_CUDA_CHECK(cudaEventRecord(o.copy_fork, st));
-                    SPDE_CUDA_CHECK(cudaStreamWaitEvent(cs, o.copy_fork, 0));
-                    SPDE_CUDA_CHECK(cudaMemcpyAsync(o.d_pool + g.off_dinv, o.h_pool + g.host_off, (size_t)g.dinv_size * sizeof(double),
-                                                    cudaMemcpyHostToDevice, cs));
-                    for (int c = (int)g.chunk_off.size() - 1; c >= 0; c--) {
-                        SPDE_CUDA_CHECK(cudaMemcpyAsync(o.d_pool + g.chunk_off[c], o.h_pool + g.host_off + (g.chunk_off[c] - g.off_dinv),
-                                                        (size_t)g.chunk_len[c] * sizeof(double), cudaMemcpyHostToDevice, cs));
-                        SPDE_CUDA_CHECK(cudaEventRecord(o.fetch_ev[c], cs));
-                    }
-                } else if (g.top) {
-                    SPDE_CUDA_CHECK(cudaMemcpyAsync(o.d_pool + g.off_dinv, o.h_pool + g.host_off, (size_t)(o.pool_size - g.off_dinv) * sizeof(double),
-                                                    cudaMemcpyHostToDevice, st));
-                } else if ((rc = scatter_and_factor(g, sg))) return rc;
+            // tables of this segment's schedules first: the host-to-device copy engine is a FIFO, a table upload queued
+            // behind the slices of the panel would hold the compute stream until the whole panel has arrived
+            Program *B = bsolve ? &o.solve_program(g, k, 1) : nullptr;
+            ZEntry *d_ze = nullptr;
+            if (fetch) {
+                if (B && (rc = sg.program(*B))) return rc;
+                if (d_Zq) {
+                    if ((rc = sg.put(o.zent.data() + g.zent0, (size_t)(g.zent1 - g.zent0), &d_ze))) return rc;
+                    if ((rc = sg.program(g.selinv))) return rc;
+                }
+                // the panel comes back slice by slice, last slice first (the order the Takahashi recursion walks the
+                // block columns), behind everything that still uses this memory
+                SPDE_CUDA_CHECK(cudaEventRecord(o.copy_fork, st));
+                SPDE_CUDA_CHECK(cudaStreamWaitEvent(cs, o.copy_fork, 0));
+                SPDE_CUDA_CHECK(cudaMemcpyAsync(o.d_pool + g.off_dinv, o.h_pool + g.host_off, (size_t)g.dinv_size * sizeof(double),
+                                                cudaMemcpyHostToDevice, cs));
+                for (int c = (int)g.chunk_off.size() - 1; c >= 0; c--) {
+                    SPDE_CUDA_CHECK(cudaMemcpyAsync(o.d_pool + g.chunk_off[c], o.h_pool + g.host_off + (g.chunk_off[c] - g.off_dinv),
+                                                    (size_t)g.chunk_len[c] * sizeof(double), cudaMemcpyHostToDevice, cs));
+                    SPDE_CUDA_CHECK(cudaEventRecord(o.fetch_ev[c], cs));
+                }
+            } else {
+                if (!g.keep) {
+                    if (g.top) {
+                        SPDE_CUDA_CHECK(cudaMemcpyAsync(o.d_pool + g.off_dinv, o.h_pool + g.host_off, (size_t)(o.pool_size - g.off_dinv) * sizeof(double),
+                                                        cudaMemcpyHostToDevice, st));
+                    } else if ((rc = scatter_and_factor(g, sg))) return rc;
+                }
+                if (B) {
+                    if ((rc = sg.program(*B))) return rc;
+                    if ((rc = issue_program_ex(p, *B, ctx, st))) return rc;
+                }
+                if (d_Zq) {
+                    if ((rc = sg.put(o.zent.data() + g.zent0, (size_t)(g.zent1 - g.zent0), &d_ze))) return rc;
+                    if ((rc = sg.program(g.selinv))) return rc;
+                }
             }
-            auto back_substitution = [&]() -> int {
-                if (!bsolve) return SPDE_OK;
-                Program &B = o.solve_program(g, k, 1);
-                int r = sg.program(B);
-                if (r) return r;
-                return issue_program_ex(p, B, ctx, st);
-            };
-            // the solve and the recursion only read the factor, so their order is free: with the panel still arriving
-            // the recursion goes first (it waits slice by slice) and the solve runs once everything is there
-            if (!fetch && (rc = back_substitution())) return rc;
             if (d_Zq) {
-                ZEntry *d_ze = nullptr;
-                if ((rc = sg.put(o.zent.data() + g.zent0, (size_t)(g.zent1 - g.zent0), &d_ze))) return rc;
-                if ((rc = sg.program(g.selinv))) return rc;
                 ExecCtx c2 = ctx;
                 c2.zent = d_ze;
                 if ((rc = issue_program_ex(p, g.selinv, c2, st))) return rc;
             }
             if (fetch) {
+                // the solve and the recursion only read the factor, so their order is free: with the panel still arriving
+                // the recursion goes first (it waits slice by slice) and the solve runs once everything is there
                 SPDE_CUDA_CHECK(cudaStreamWaitEvent(st, o.fetch_ev[0], 0));
-                if ((rc = back_substitution())) return rc;
+                if (B && (rc = issue_program_ex(p, *B, ctx, st))) return rc;
             }
         }
     }
