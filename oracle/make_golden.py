@@ -52,6 +52,10 @@ CASES = [
     # separable space-time model Q = Qt (x) Qs (the reference ignores mod0 for this family)
     ("sep_ani_bc3", "seperable-spatial-temporal", False, True, 3, (8, 7, 4), None, "whittle-matern", False),
     ("sep_ani_bc1_ext", "seperable-spatial-temporal", False, True, 1, (7, 6, 3), 1, "whittle-matern", False),
+    # half-angle / isotropic separable classes: Qt = sigma * tridiag(-a, 1 + a^2, -a) is built with a hard-coded
+    # range(10) (seperable_spatial_temporal_ha2D.py:205-224), so they are only defined for T = 10
+    ("sep_ha_bc3", "seperable-spatial-temporal", True, True, 3, (7, 6, 10), None, "whittle-matern", False),
+    ("sep_iso_bc1_ext", "seperable-spatial-temporal", False, False, 1, (6, 5, 10), 1, "whittle-matern", False),
 ]
 
 

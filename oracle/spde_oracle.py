@@ -497,14 +497,31 @@ class OracleSPDE:
 
 
 class OracleSeparable(OracleSPDE):
-    """Restatement of ``SeperableSpatialTemporal2D`` (``seperable_spatial_temporal2D.py:64-122, 186-211``):
-    ``Q = kron(Qt, Qs)``, ``Qs`` the spatially varying anisotropic Whittle-Matern precision, ``Qt`` AR(1).
-    ``par = [kappa x9, gamma x9, vx x9, vy x9, log rho, log tau]``; ``logLike`` / ``logLike_exact`` are inherited (the
+    """Restatement of the separable classes ``Q = kron(Qt, Qs)``, ``Qs`` a spatially varying Whittle-Matern precision:
+
+    * ``variant="ani"``: ``SeperableSpatialTemporal2D`` (``seperable_spatial_temporal2D.py:64-122, 186-211``), ``Qt`` AR(1)
+      in ``rho``; ``par = [kappa x9, gamma x9, vx x9, vy x9, log rho, log tau]``;
+    * ``variant="ha"``: ``SeperableSpatialTemporalHa2D`` (``seperable_spatial_temporal_ha2D.py:70-138, 202-226``), half-angle
+      ``H``, ``Qt = sigma tridiag(-a, 1 + a^2, -a)`` with ``sigma`` alone in the two corners;
+      ``par = [kappa x9, gamma x9, vx x9, vy x9, a, log sigma, log tau]``, ``dQ`` ends with ``kron(dQt/da, Qs)`` and ``Q``;
+    * ``variant="iso"``: ``SeperableSpatialTemporalIDiffusion2D`` (``seperable_spatial_temporal_idiffusion2D.py:64-102,
+      166-190``), isotropic ``H``; ``par = [kappa x9, gamma x9, a, log sigma, log tau]``.
+
+    The ``ha`` / ``iso`` classes fill ``Qt`` with a hard-coded ``range(10)`` (``..._ha2D.py:205,216``): they are defined for
+    ``T = 10`` only, which is what this restatement insists on.  ``logLike`` / ``logLike_exact`` are inherited (the
     reference's ``logLike`` body is the common one, ``:125-170``)."""
 
-    def __init__(self, grid, par=None, bc: int = 3):
-        super().__init__("var-whittle-matern-anisotropic-2D", grid, None, None, bc)
-        self.type = "seperable-spatial-temporal-ani-2D-bc%d" % bc
+    KEYS = {"ani": ("var-whittle-matern-anisotropic-2D", "seperable-spatial-temporal-ani-2D-bc%d", 36),
+            "ha": ("var-whittle-matern-ha-2D", "seperable-spatial-temporal-ha-2D-bc%d", 36),
+            "iso": ("var-whittle-matern-isotropic-2D", "seperable-spatial-temporal-2D-bc%d", 18)}
+
+    def __init__(self, grid, par=None, bc: int = 3, variant: str = "ani"):
+        key, typ, self.nsp = self.KEYS[variant]
+        super().__init__(key, grid, None, None, bc)
+        self.variant = variant
+        self.type = typ % bc
+        if variant != "ani" and grid.T != 10:
+            raise ValueError("the reference builds Qt of this class for T = 10 only")
         if par is not None:
             self.setQ(par)
 
@@ -524,18 +541,44 @@ class OracleSeparable(OracleSPDE):
                 res[i, i + 1] = off
         return sparse.csc_matrix(res)
 
+    @staticmethod
+    def makeQt_a(a, sigma, T, diff=0):
+        """``makeQt(a, sigma)`` of the ha / idiffusion classes; ``diff=1`` is the derivative with respect to ``a``."""
+        res = np.zeros((T, T))
+        for i in range(T):
+            ends = i == 0 or i == T - 1
+            if diff == 1:
+                res[i, i] = 0 if ends else 2 * a * sigma
+                off = -sigma
+            else:
+                res[i, i] = sigma if ends else (1 + a ** 2) * sigma
+                off = -a * sigma
+            if i > 0:
+                res[i, i - 1] = off
+            if i < T - 1:
+                res[i, i + 1] = off
+        return sparse.csc_matrix(res)
+
     def makeQ(self, par, grad=True):
         par = np.asarray(par, dtype="float64")
-        T = self.grid.T
-        Qs, _, dQs = self._makeQ_spatial(np.hstack([par[:36], par[-1]]), grad)
-        rho = np.exp(par[36])
-        Qt = self.makeQt(rho, T)
+        T, k = self.grid.T, self.nsp
+        Qs, _, dQs = self._makeQ_spatial(np.hstack([par[:k], par[-1]]), grad)
+        if self.variant == "ani":
+            rho = np.exp(par[k])
+            Qt = self.makeQt(rho, T)
+        else:
+            apar, sigma = par[k], np.exp(par[k + 1])
+            Qt = self.makeQt_a(apar, sigma, T)
         Q = sparse.kron(Qt, Qs).tocsc()
         Q_fac = cholesky(Q)
         if not grad:
             return Q, Q_fac, None
         dQ = [sparse.kron(Qt, d).tocsc() for d in dQs]
-        dQ.append(sparse.kron(self.makeQt(rho, T, diff=1), Qs).tocsc())
+        if self.variant == "ani":
+            dQ.append(sparse.kron(self.makeQt(rho, T, diff=1), Qs).tocsc())
+        else:
+            dQ.append(sparse.kron(self.makeQt_a(apar, sigma, T, diff=1), Qs).tocsc())
+            dQ.append(Q)          # log sigma: Qt is proportional to sigma
         return Q, Q_fac, dQ
 
     def setQ(self, par=None):

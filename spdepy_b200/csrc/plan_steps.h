@@ -158,7 +158,8 @@ struct LevelBuilder {
                         if (lower && (ti + 1) * BM - 1 < tj * BN) continue;
                         prog.tiles.push_back(TileRef{id, ti, tj, 0});
                     }
-                prog.flops += 2.0 * t.M * t.N * t.K * (lower ? 0.5 : 1.0);
+                // lower: the trapezoid on and below the diagonal of an M x N block (M >= N)
+                prog.flops += 2.0 * t.K * (lower ? (double)t.M * t.N - 0.5 * t.N * std::min(t.M, t.N) : (double)t.M * t.N);
             }
         }
         L.ntasks = (int)(prog.gemm.size() - L.task0);

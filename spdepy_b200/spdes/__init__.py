@@ -1,8 +1,7 @@
 """Model classes with the reference's names and ``spde_init`` dispatcher (``spdes/__init__.py:1-105``).
 
 Every class is a configuration of :class:`spdepy_b200.spdes.base.SPDE2D`; the table below is the
-reference's App. B parameter layout.  Families that are not wired yet raise
-``NotImplementedError`` at construction instead of silently doing something else."""
+reference's App. B parameter layout; the three separable classes live in ``separable.py``."""
 from .base import SPDE2D
 
 N9 = 9
@@ -100,10 +99,8 @@ def spde_init(model, grid, parameters=None, ani=True, ha=True, bc=3, mod0=None):
                 return cls(par=parameters, grid=grid, bc=bc, mod0=mod0)
             return cls(par=parameters, grid=grid, bc=bc)
     if model in _NEXT or model in _NEXT.values():
-        if ha or not ani:
-            raise NotImplementedError("seperable-spatial-temporal: only the anisotropic class is wired; the reference's ha / "
-                                      "idiffusion variants build Qt with a hard-coded range(10) "
-                                      "(seperable_spatial_temporal_ha2D.py:205-211)")
-        from .separable import SeperableSpatialTemporal2D
-        return SeperableSpatialTemporal2D(par=parameters, grid=grid, bc=bc)
+        from . import separable as sep
+        cls = (sep.SeperableSpatialTemporalHa2D if ha else
+               (sep.SeperableSpatialTemporal2D if ani else sep.SeperableSpatialTemporalIDiffusion2D))
+        return cls(par=parameters, grid=grid, bc=bc)
     raise AssertionError("Model not implemented")

@@ -1,7 +1,16 @@
-"""Separable space-time model ``Q = Qt (x) Qs`` (``seperable_spatial_temporal2D.py``): AR(1) precision in time,
-spatially varying anisotropic Whittle-Matern precision in space.
+"""Separable space-time models ``Q = Qt (x) Qs`` (``seperable_spatial_temporal2D.py``, ``..._ha2D.py``,
+``..._idiffusion2D.py``): tridiagonal precision in time, spatially varying Whittle-Matern precision in space.
 
-Reference layout (``:30-38``): ``par = [kappa x9, gamma x9, vx x9, vy x9, log rho, log tau]`` (Np hard-coded 9).
+Reference layouts (Np hard-coded 9):
+
+* anisotropic (``seperable_spatial_temporal2D.py:30-38``): ``par = [kappa x9, gamma x9, vx x9, vy x9, log rho, log tau]``,
+  ``Qt`` the AR(1) precision in ``rho`` (``:186-211``);
+* half-angle (``seperable_spatial_temporal_ha2D.py:26-35``): ``par = [kappa x9, gamma x9, vx x9, vy x9, a, log sigma, log tau]``;
+* isotropic (``seperable_spatial_temporal_idiffusion2D.py:30-36``): ``par = [kappa x9, gamma x9, a, log sigma, log tau]``;
+  for both, ``Qt = sigma tridiag(-a, 1 + a^2, -a)`` with ``sigma`` alone in the two corners, its derivative list is
+  ``[kron(dQt/da, Qs), Q]`` (``..._ha2D.py:133-136``), and the reference fills ``Qt`` with a hard-coded ``range(10)``
+  (``..._ha2D.py:205,216``): the classes exist for ``T = 10`` only and say so here instead of returning a singular matrix.
+
 ``Q`` has 75 entries per row (5x5 blocks to t-1, t and t+1), the third slot layout of the C ABI
 (``SPDE_PATTERN_KRON``); the supernodal plan, the solves, the Takahashi pass and the reductions are the same kernels
 as for the advection-diffusion family.  The spatial factor ``Qs = As^T Dv^-1 As`` (``:78-80``) is assembled by the
@@ -9,10 +18,7 @@ var-Whittle-Matern configuration of :class:`SPDE2D`, which also owns the chain r
 weights on ``Q`` are collapsed over time with ``Qt`` (``spde_kron_reduce``) and handed to its adjoint pass.
 
 The prior never needs a 3-D factorisation: ``logdet Q = Ns logdet Qt + T logdet Qs`` and
-``tr(Q^-1 dQ_i) = T tr(Qs^-1 dQs_i)`` (spatial parameters), ``Ns tr(Qt^-1 dQt)`` (log rho).
-Only the anisotropic class is wired: the reference's ``ha`` and ``idiffusion`` variants build their ``Qt`` derivative
-with a hard-coded ``range(10)`` and append ``Q`` itself as a derivative (``seperable_spatial_temporal_ha2D.py:205-211,
-135-136``), which has no well-defined restatement.
+``tr(Q^-1 dQ_i) = T tr(Qs^-1 dQs_i)`` (spatial parameters), ``Ns tr(Qt^-1 dQt_j)`` (temporal parameters).
 """
 from __future__ import annotations
 
@@ -33,6 +39,19 @@ class _SpatialFactor(SPDE2D):
     default_own = ([-1] * 9, [-1] * 9, [0.1] * 9, [0.1] * 9)
 
 
+class _SpatialFactorHa(_SpatialFactor):
+    """Half-angle H = gamma (cosh|v| I + sinh|v|/|v| [[vx, vy], [vy, -vx]]) (``seperable_spatial_temporal_ha2D.py:82-89``)."""
+    name = "seperable-spatial-temporal-ha-2D[Qs]"
+    Hkind = "ha"
+
+
+class _SpatialFactorIso(_SpatialFactor):
+    """Isotropic H = gamma I (``seperable_spatial_temporal_idiffusion2D.py:74``)."""
+    name = "seperable-spatial-temporal-2D[Qs]"
+    Hkind = "iso"
+    default_own = ([-1] * 9, [-1] * 9)
+
+
 def qt_coeffs(rho: float, diff: int = 0):
     """(d0, d1, e) of the tridiagonal ``makeQt`` (``:186-211``): diagonal (d0, d1, ..., d1, d0), off-diagonal e;
     ``diff=1`` is the derivative with respect to log rho."""
@@ -40,6 +59,14 @@ def qt_coeffs(rho: float, diff: int = 0):
         return (2 * rho ** 2 / (1 - rho ** 2) ** 2, 4 * rho ** 2 / (1 - rho ** 2) ** 2,
                 -rho * (1 + rho ** 2) / (1 - rho ** 2) ** 2)
     return 1 / (1 - rho ** 2), (1 + rho ** 2) / (1 - rho ** 2), -rho / (1 - rho ** 2)
+
+
+def qt_coeffs_a(a: float, sigma: float, diff: int = 0):
+    """(d0, d1, e) of ``makeQt(a, sigma)`` of the ha / idiffusion classes (``seperable_spatial_temporal_ha2D.py:202-226``);
+    ``diff=1`` is the derivative with respect to ``a``."""
+    if diff == 1:
+        return 0.0, 2 * a * sigma, -sigma
+    return sigma, (1 + a ** 2) * sigma, -a * sigma
 
 
 def _qt_dense(T, c):
@@ -58,10 +85,13 @@ class SeperableSpatialTemporal2D:
     """Drop-in for ``spdepy.spdes.seperable_spatial_temporal2D.SeperableSpatialTemporal2D`` (same spelling)."""
     timed = True
     collapse_prior = True
+    _spatial_cls = _SpatialFactor
+    _type = "seperable-spatial-temporal-ani-2D-bc%d"
+    _nsp = 36                 # spatial parameters; the temporal ones follow, log tau is last
 
     def __init__(self, grid, par=None, bc=3) -> None:
         self.grid = grid
-        self.type = "seperable-spatial-temporal-ani-2D-bc%d" % bc
+        self.type = self._type % bc
         self.Q = None
         self.Q_fac = None
         self.data = None
@@ -74,12 +104,16 @@ class SeperableSpatialTemporal2D:
         M, N, T = grid.shape[0], grid.shape[1], grid.T
         if T < 2:
             raise ValueError("the separable space-time model needs at least two time steps")
+        self._check_T(T)
         self.engine = Engine.get(M, N, T, bc, pat=1)
-        self.spatial = _SpatialFactor(grid, bc=bc)
+        self.spatial = self._spatial_cls(grid, bc=bc)
         if par is None:
             self.setPars(self._default_par())
         else:
             self.setQ(par=par)
+
+    def _check_T(self, T):
+        pass
 
     # ------------------------------------------------------------------ parameters (:28-47)
     @staticmethod
@@ -94,6 +128,11 @@ class SeperableSpatialTemporal2D:
         self.kappa, self.gamma = par[0:9], par[9:18]
         self.vx, self.vy = par[18:27], par[27:36]
         self.rho, self.tau = par[36], par[37]
+
+    def _qt_list(self, par):
+        """Coefficients (d0, d1, e) of ``Qt`` and of its derivative for every temporal parameter, in ``par`` order."""
+        rho = float(np.exp(par[36]))
+        return qt_coeffs(rho), [qt_coeffs(rho, 1)]            # d / d log rho
 
     def initFit(self, data, **kwargs):
         data = np.asarray(data, dtype="float64")
@@ -139,12 +178,11 @@ class SeperableSpatialTemporal2D:
     # ------------------------------------------------------------------ assembly
     def _assemble(self, par):
         par = np.asarray(par, dtype="float64")
-        sp_par = np.hstack([par[:36], par[-1]])
+        sp_par = np.hstack([par[:self._nsp], par[-1]])
         st_s = self.spatial._assemble(sp_par)                 # kappa, A9 = Dv Dk - Ah(Hs), Qs = As^T Dv^-1 As
-        rho = float(np.exp(par[36]))
-        qt = qt_coeffs(rho)
+        qt, dqt = self._qt_list(par)
         Q = self.engine.fill_kron(st_s["Q"], *qt)
-        return {"par": par, "spatial": st_s, "rho": rho, "qt": qt, "Q": Q, "joint": False}
+        return {"par": par, "spatial": st_s, "qt": qt, "dqt": dqt, "Q": Q, "joint": False}
 
     def makeQ(self, par, grad=True):
         """``(Q, Q_fac)`` or ``(Q, Q_fac, dQ)`` as the reference (``:64-122``); ``dQ`` are lazy operators."""
@@ -160,23 +198,25 @@ class SeperableSpatialTemporal2D:
         ops = []
         for op in self.spatial._lazy_dQ(st["spatial"]):           # kron(Qt, dQs_i)
             ops.append(_KronDQ(self, st, op, None))
-        ops.append(_KronDQ(self, st, None, qt_coeffs(st["rho"], 1)))      # kron(dQt, Qs)
+        for dqt in st["dqt"]:
+            ops.append(_KronDQ(self, st, None, dqt))              # kron(dQt_j, Qs)
         return ops
 
     # ------------------------------------------------------------------ gradient contraction
     def _grad_from_weights(self, st, W, prior=None):
-        """sum(W .* dQ_i) for the 37 own parameters; ``prior = {"c": c, "Zs": Z of Qs}`` adds ``c d logdet Q``."""
+        """sum(W .* dQ_i) for the own parameters (all but log tau); ``prior = {"c": c, "Zs": Z of Qs}`` adds
+        ``c d logdet Q``."""
         eng = self.engine
         Wd = eng.kron_reduce(W, *st["qt"])
-        dqt = qt_coeffs(st["rho"], 1)
-        g_rho = Engine.dot(W, eng.fill_kron(st["spatial"]["Q"], *dqt))
+        g_t = [Engine.dot(W, eng.fill_kron(st["spatial"]["Q"], *dqt)) for dqt in st["dqt"]]
         if prior is not None:
             c = prior["c"]
             Wd = Wd + (c * eng.T) * prior["Zs"]
-            Qt, dQt = _qt_dense(eng.T, st["qt"]), _qt_dense(eng.T, dqt)
-            g_rho += c * eng.Ns * float(np.trace(np.linalg.solve(Qt, dQt)))
+            Qt = _qt_dense(eng.T, st["qt"])
+            for j, dqt in enumerate(st["dqt"]):
+                g_t[j] += c * eng.Ns * float(np.trace(np.linalg.solve(Qt, _qt_dense(eng.T, dqt))))
         out = list(self.spatial._grad_from_weights(st["spatial"], Wd))
-        out.append(g_rho)
+        out.extend(g_t)
         return out
 
     def _prior_collapsed(self, st, want_grad):
@@ -253,6 +293,69 @@ class SeperableSpatialTemporal2D:
         g_par[:len(gi)] = gi
         g_par[-1] = nobs * r / 2 - 1 / 2 * tr_tau * r - tau / 2 * resid
         return -like / (nobs * r), -g_par / (nobs * r)
+
+
+class SeperableSpatialTemporalHa2D(SeperableSpatialTemporal2D):
+    """Drop-in for ``spdepy.spdes.seperable_spatial_temporal_ha2D.SeperableSpatialTemporalHa2D``: half-angle diffusion,
+    ``Qt = sigma tridiag(-a, 1 + a^2, -a)``; ``par = [kappa x9, gamma x9, vx x9, vy x9, a, log sigma, log tau]``."""
+    _spatial_cls = _SpatialFactorHa
+    _type = "seperable-spatial-temporal-ha-2D-bc%d"
+
+    def _check_T(self, T):
+        if T != 10:
+            raise ValueError("%s: the reference fills Qt with a hard-coded range(10) (seperable_spatial_temporal_ha2D.py:"
+                             "205,216), so the class is defined for T = 10 only (got T = %d)" % (type(self).__name__, T))
+
+    @staticmethod
+    def _default_par():
+        return np.hstack([[-1] * 9, [-1] * 9, [0.1] * 9, [0.1] * 9, 0.1, 1, np.log(100)]).astype("float64")
+
+    def getPars(self, *args, **kwargs) -> np.ndarray:
+        return np.hstack([self.kappa, self.gamma, self.vx, self.vy, self.a, self.sigma, self.tau]).astype("float64")
+
+    def setPars(self, par) -> None:
+        par = np.array(par, dtype="float64")
+        self.kappa, self.gamma = par[0:9], par[9:18]
+        self.vx, self.vy = par[18:27], par[27:36]
+        self.a, self.sigma, self.tau = par[36], par[37], par[38]
+
+    def _qt_list(self, par):
+        a, sigma = float(par[self._nsp]), float(np.exp(par[self._nsp + 1]))
+        qt = qt_coeffs_a(a, sigma)
+        return qt, [qt_coeffs_a(a, sigma, 1), qt]             # d / d a;  d / d log sigma = Qt itself
+
+    def print(self, par):
+        return ("| κ = %2.2f" % (np.exp(par[0:9]).mean()) + ", γ = %2.2f" % (np.exp(par[9:18]).mean())
+                + ", vx = %2.2f" % ((par[18:27]).mean()) + ", vy = %2.2f" % ((par[27:36]).mean())
+                + ", a = %2.2f" % (par[36]) + ", σ = %2.2f" % (np.exp(par[37])) + ", τ = %2.2f" % (np.exp(par[38])))
+
+    def makeQt(self, a, sigma, T=10, diff=0):
+        from scipy import sparse
+        return sparse.csc_matrix(_qt_dense(T, qt_coeffs_a(a, sigma, diff)))
+
+
+class SeperableSpatialTemporalIDiffusion2D(SeperableSpatialTemporalHa2D):
+    """Drop-in for ``spdepy.spdes.seperable_spatial_temporal_idiffusion2D.SeperableSpatialTemporalIDiffusion2D``:
+    isotropic diffusion; ``par = [kappa x9, gamma x9, a, log sigma, log tau]``."""
+    _spatial_cls = _SpatialFactorIso
+    _type = "seperable-spatial-temporal-2D-bc%d"
+    _nsp = 18
+
+    @staticmethod
+    def _default_par():
+        return np.hstack([[-1] * 9, [-1] * 9, 0.1, 1, np.log(100)]).astype("float64")
+
+    def getPars(self, *args, **kwargs) -> np.ndarray:
+        return np.hstack([self.kappa, self.gamma, self.a, self.sigma, self.tau]).astype("float64")
+
+    def setPars(self, par) -> None:
+        par = np.array(par, dtype="float64")
+        self.kappa, self.gamma = par[0:9], par[9:18]
+        self.a, self.sigma, self.tau = par[18], par[19], par[20]
+
+    def print(self, par):
+        return ("| κ = %2.2f" % (np.exp(par[0:9]).mean()) + ", γ = %2.2f" % (np.exp(par[9:18]).mean())
+                + ", a = %2.2f" % (par[18]) + ", σ = %2.2f" % (np.exp(par[19])) + ", τ = %2.2f" % (np.exp(par[20])))
 
 
 class _KronDQ:

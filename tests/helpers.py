@@ -57,7 +57,7 @@ def make_oracle(d):
     import spde_oracle as so
     g, g0 = make_grids(d)
     if d["spde"] == "seperable-spatial-temporal":
-        return so.OracleSeparable(g, bc=d["bc"])
+        return so.OracleSeparable(g, bc=d["bc"], variant="ha" if d["ha"] else ("ani" if d["ani"] else "iso"))
     mod0 = None
     if g0 is not None:
         mod0 = so.OracleSPDE(spec_key(d["mod0_spde"], d["ha"], d["ani"]), g0, bc=d["bc"], par=d["mod0_par"])

@@ -133,7 +133,7 @@ def test_not_positive_definite_raises():
 
 
 @pytest.mark.parametrize("name", ["wm_ani_bc1_ext", "varwm_ani_bc2", "ad_ani_bc3_q0", "ad_ha_bc1_q0", "vavd_ani_bc1_ext_q0",
-                                  "sep_ani_bc3"])
+                                  "sep_ani_bc3", "sep_ha_bc3", "sep_iso_bc1_ext"])
 def test_lazy_dQ_operators_vs_oracle(name):
     """makeQ(grad=True) returns dQ as lazy operators; dQ[i] @ X must equal the reference's explicit matrices."""
     d = load_golden(name)

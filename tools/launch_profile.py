@@ -31,7 +31,9 @@ for prog, pname in ((0, "factor"), (3, "selinv")):
     P = pe.Program(plan, prog)
     ms = plan.export(prog, 7, "f4")
     g = P.gemm
-    fl = 2.0 * g["M"] * g["N"] * g["K"] * np.where(g["flags"] & pe.GF_LOWER, 0.5, 1.0)
+    M_, N_ = g["M"].astype(np.float64), g["N"].astype(np.float64)
+    # lower: the trapezoid on and below the diagonal of an M x N block (M >= N), not half of it
+    fl = 2.0 * g["K"] * np.where(g["flags"] & pe.GF_LOWER, M_ * N_ - 0.5 * N_ * np.minimum(M_, N_), M_ * N_)
     rows = []
     for i, L in enumerate(P.launches):
         if L["kind"] != 0:
