@@ -92,14 +92,18 @@ class Model:
         self.mu = np.zeros(self.Q.shape[0]) if mu is None else self.grid.getS().T @ mu
 
     # ------------------------------------------------------------------ model.py:73-87
-    def sample(self, n=1, simple=False, seed=None) -> np.ndarray:
+    def sample(self, n=1, simple=False, seed=None, cols=None) -> np.ndarray:
+        """``cols`` (a slice, optional) restricts the work to those columns of the same ``n``-column draw: the
+        column-block shard of one rank (``spdepy_b200.parallel.sample_sharded``)."""
         if seed is None:
             seed = np.random.randint(100)
         eng = self.mod.engine
         if self.useCov:
-            return self._sample_bordered(n, simple, seed)
+            return self._sample_bordered(n, simple, seed, cols)
         N = eng.n
         z = np.random.default_rng(seed).normal(size=N * n).reshape(N, n)
+        if cols is not None:
+            z = np.ascontiguousarray(z[:, cols])
         self.Q_fac = eng.factorize(0, self._Qdev)
         x = eng.solve(0, to_dev(z), 10)                         # P^T L^-T z
         x += to_dev(self.mu)[:, None]
@@ -146,10 +150,12 @@ class Model:
         nodes = np.asarray(self.grid.obs_nodes(idx), dtype=np.int64)
         return X, nodes
 
-    def _sample_bordered(self, n, simple, seed):
+    def _sample_bordered(self, n, simple, seed, cols=None):
         eng, bd = self.mod.engine, self._border
         N, k = eng.n, bd.k
         z = np.random.default_rng(seed).normal(size=(N + k) * n).reshape(N + k, n)
+        if cols is not None:
+            z = np.ascontiguousarray(z[:, cols])
         self.Q_fac = eng.factorize(0, self._Qdev)
         Y, L22 = bd.factor(eng)
         # [[L11, 0], [Y^T, L22]]^T u = z  ->  u2 = L22^-T z2,  u1 = L11^-T (z1 - Y u2);  x = [P^T u1; u2]

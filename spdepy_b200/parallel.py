@@ -70,3 +70,27 @@ def column_block(n_cols: int, rank: int | None = None, world: int | None = None)
     world = w if world is None else world
     per = (n_cols + world - 1) // world
     return slice(min(rank * per, n_cols), min((rank + 1) * per, n_cols))
+
+
+def sample_sharded(model, n: int, seed: int, simple: bool = True, gather: bool = True):
+    """``Model.sample(n, seed=seed)`` with the ``n`` columns split into contiguous blocks over the ranks: every rank
+    factorises the same precision (replicated, as everywhere on this path), draws the same seeded ``z`` and solves only
+    its own columns (``Model.sample(..., cols=...)``).  With ``gather`` one all-gather assembles the full block on
+    every rank, otherwise each rank keeps ``(columns, block)``."""
+    rank, world = _world()
+    cols = column_block(n, rank, world)
+    mine = np.asarray(model.sample(n=n, simple=simple, seed=seed, cols=cols), dtype=np.float64)
+    if not gather:
+        return cols, mine
+    if world == 1:
+        return mine
+    per = (n + world - 1) // world
+    pad = torch.zeros(mine.shape[0], per, dtype=torch.float64, device=_buffer_device())
+    pad[:, :mine.shape[1]] = torch.as_tensor(mine, device=pad.device)
+    parts = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(parts, pad)
+    out = np.empty((mine.shape[0], n))
+    for r in range(world):
+        c = column_block(n, r, world)
+        out[:, c] = parts[r][:, :c.stop - c.start].cpu().numpy()
+    return out

@@ -67,6 +67,8 @@ def test_sample_update_against_oracle(name):
     finally:
         so.set_factor(None, None)
     assert relerr(X, Xo) < 1e-9
+    # a column block of the same draw (the shard of one rank, parallel.sample_sharded)
+    assert relerr(mod.sample(n=4, seed=3, simple=True, cols=slice(1, 3)), Xo[:, 1:3]) < 1e-9
     mod.update(y=d["data"][:, 0], idx=d["idx"])
     assert relerr(mod.mu, d["upd_mu"]) < 1e-9
     assert relerr(mod.getQ().diagonal(), d["upd_Qdiag"]) < 1e-13

@@ -26,6 +26,15 @@ WORKER = textwrap.dedent("""
     assert np.allclose(g, 3 * np.array([1.0, 4.0, 1.0]), atol=1e-6)
     blocks = [par.column_block(10, r, world) for r in range(world)]
     assert sum(b.stop - b.start for b in blocks) == 10
+    class Stub:                      # Model.sample contract: same seeded draw, only the requested columns
+        def sample(self, n, simple, seed, cols):
+            z = np.random.default_rng(seed).normal(size=6 * n).reshape(6, n)
+            return 2.0 * z[:, cols] + 1.0
+    full = par.sample_sharded(Stub(), 7, seed=3)
+    ref = 2.0 * np.random.default_rng(3).normal(size=42).reshape(6, 7) + 1.0
+    assert full.shape == (6, 7) and np.array_equal(full, ref)
+    cols, mine = par.sample_sharded(Stub(), 7, seed=3, gather=False)
+    assert np.array_equal(mine, ref[:, cols]) and mine.shape[1] in (3, 4)
     dist.barrier()
     dist.destroy_process_group()
     print("rank", rank, "ok")
