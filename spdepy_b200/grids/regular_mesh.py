@@ -290,6 +290,28 @@ class _RegularMesh:
         return scl[:, None] * ww[src]
 
 
+    def assimilate_adv(self, we, wn) -> np.ndarray:
+        """Cell-centred velocities (east, north components on the ``M x N`` cells, x fastest) -> the four face values
+        ``(E, N, W, S)`` the covariate-driven advection classes take: mean of the two cells sharing the face, the cell's
+        own value on the boundary, then the extension ramp (``spat2Dtemp_regular_mesh.py:277-344``; the reference builds
+        four dense ``(MN)^2`` averaging matrices for this)."""
+        M, N = self.M, self.N
+        we = np.asarray(we, dtype=np.float64).reshape(N, M)
+        wn = np.asarray(wn, dtype=np.float64).reshape(N, M)
+        ww = np.zeros((M * N, 4))
+        ww[:, 0] = ((we + np.concatenate([we[:, 1:], we[:, -1:]], axis=1)) / 2).reshape(-1)
+        ww[:, 1] = ((wn + np.concatenate([wn[1:], wn[-1:]], axis=0)) / 2).reshape(-1)
+        ww[:, 2] = ((we + np.concatenate([we[:, :1], we[:, :-1]], axis=1)) / 2).reshape(-1)
+        ww[:, 3] = ((wn + np.concatenate([wn[:1], wn[:-1]], axis=0)) / 2).reshape(-1)
+        return self.advBound(ww)
+
+    def idx2pos(self, idx):
+        return None          # a stub in the reference as well (spat2Dtemp_regular_mesh.py:70-71)
+
+    def plot(self, value):
+        return None          # a stub in the reference as well (:394-395)
+
+
 class GridS(_RegularMesh):
     timed = False
 

@@ -1,0 +1,29 @@
+"""Host grid helpers on the caller side of the path against the unmodified reference (fixtures written by
+oracle/make_golden_grid.py): ``Grid.assimilate_adv`` -- cell-centred currents to the face velocities of the
+covariate-driven advection classes, with the extension ramp -- bit for bit."""
+import os
+
+import numpy as np
+
+from spdepy_b200.grids import grid
+
+G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "grid", "assimilate_adv.npz"))
+
+
+def test_assimilate_adv_matches_reference():
+    for c, (M, N, T, ext) in enumerate(G["cases"]):
+        g = grid(x=np.linspace(0, 3, M), y=np.linspace(0, 2, N), t=np.linspace(0, 1, T), extend=None if ext < 0 else int(ext))
+        ww = g.assimilate_adv(G["we%d" % c], G["wn%d" % c])
+        assert ww.shape == G["ww%d" % c].shape == (g.Ns, 4)
+        assert np.array_equal(ww, G["ww%d" % c])
+
+
+def test_assimilate_adv_constant_field():
+    """A constant current stays constant on every face of the interior and is ramped to zero across the extension."""
+    g = grid(x=np.linspace(0, 3, 6), y=np.linspace(0, 2, 5), t=np.linspace(0, 1, 2), extend=2)
+    ww = g.assimilate_adv(np.full(30, 2.0), np.full(30, -1.0))
+    inner = g.obs_nodes()[:30] if hasattr(g, "obs_nodes") else None
+    assert np.all((ww[:, 0] >= 0) & (ww[:, 0] <= 2.0)) and np.all((ww[:, 1] <= 0) & (ww[:, 1] >= -1.0))
+    if inner is not None:
+        assert np.array_equal(ww[inner], np.tile([2.0, -1.0, 2.0, -1.0], (30, 1)))
+    assert np.array_equal(ww[0], np.zeros(4))          # outer corner of the extension
