@@ -26,3 +26,29 @@ if __name__ == "__main__":
         out["we%d" % c], out["wn%d" % c], out["ww%d" % c] = we, wn, g.assimilate_adv(we, wn)
     np.savez_compressed(os.path.join(OUT, "assimilate_adv.npz"), **out)
     print("wrote", len(CASES), "cases")
+
+
+def transdiff_cases():
+    """``transDiff`` of the ten half-angle classes of the unmodified reference at perturbed default parameters."""
+    sp = rh.load_reference()
+    x, y, t = np.linspace(0, 3, 8), np.linspace(0, 2, 7), np.linspace(0, 1, 10)
+    rng = np.random.default_rng(21)
+    out = {}
+    names = ["whittle-matern", "var-whittle-matern", "advection-diffusion", "advection-var-diffusion", "cov-advection-diffusion",
+             "cov-advection-var-diffusion", "var-advection-diffusion", "var-advection-var-diffusion", "seperable-spatial-temporal"]
+    for name in names:
+        timed = "whittle" not in name
+        g = sp.grid(x=x, y=y, t=t) if timed else sp.grid(x=x, y=y)
+        mod = sp.model(grid=g, spde=name, ha=True, bc=3).mod
+        par = np.array(mod.getPars(), dtype="float64")
+        par = par + 0.2 * rng.normal(size=par.size)
+        mod.transDiff(par)
+        out[name + "|par"] = par
+        for k in ("tgamma", "tvx", "tvy"):
+            out[name + "|" + k] = np.asarray(getattr(mod, k), dtype="float64")
+    np.savez_compressed(os.path.join(OUT, "transdiff.npz"), **out)
+    print("wrote transDiff of", len(names), "classes")
+
+
+if __name__ == "__main__":
+    transdiff_cases()

@@ -114,6 +114,29 @@ class SPDE2D:
             return np.hstack([self._own, self.tau]).astype("float64")
         return np.hstack([self._own, self.mod0.getPars()[:-1], self.tau]).astype("float64")
 
+    def transDiff(self, par=None):
+        """Half-angle classes only: the (gamma, vx, vy) of the equivalent ``gamma I + v v^T`` parametrisation, left in
+        ``self.tgamma / tvx / tvy`` as the reference does.  Constant-coefficient form ``whittle_matern_ha2D.py:37-45``
+        (it scales ``tvx, tvy`` with ``exp(par[0])``; reproduced), spline-field form ``advection_var_ha_diffusion2D.py:
+        46-58``; ``VarWhittleMaternHa2D`` uses the constant form on its first four entries (``var_whittle_matern_ha2D.py:
+        37-45``; reproduced)."""
+        if self.Hkind != "ha":
+            raise AttributeError("%s has no transDiff (half-angle classes only)" % type(self).__name__)
+        par = self.getPars() if par is None else np.asarray(par, dtype="float64")
+        if self.Hvar and self.timed:
+            g0, vx, vy = np.exp(self.grid.evalB(par[9:18])), self.grid.evalB(par[18:27]), self.grid.evalB(par[27:36])
+            g1 = g0
+        else:
+            # the scale under the square roots is exp(par[0]) in four classes and exp(par[1]) in the cov- / var-advection
+            # ones (cov_advection_ha_diffusion2D.py:54-56, var_advection_ha_diffusion2D.py:53-55)
+            g0, g1, vx, vy = np.exp(par[1]), np.exp(par[1] if self.wkind in ("cov", "var") else par[0]), par[2], par[3]
+        aV = np.sqrt(vx ** 2 + vy ** 2)
+        cosh_aV = (np.exp(aV) + np.exp(-aV)) / 2
+        sinh_aV = (np.exp(aV) - np.exp(-aV)) / 2
+        self.tgamma = g0 * (cosh_aV - sinh_aV)
+        self.tvx = np.sqrt(g1 * sinh_aV / aV * (vx + aV))
+        self.tvy = np.sqrt(g1 * sinh_aV / aV * (-vx + aV))
+
     def setPars(self, par) -> None:
         par = np.array(par, dtype="float64")
         self._own = par[:self.n_own].copy()
@@ -174,13 +197,15 @@ class SPDE2D:
         if "vx" in p:
             s += ", vx = %2.2f" % np.mean(p["vx"]) + ", vy = %2.2f" % np.mean(p["vy"])
         if self.wkind == "cov":
-            s += ", λ = %2.2f" % p["w"][0]
+            # the constant-coefficient classes print the multiplier itself, the spline-field ones its exponential
+            # (cov_advection_diffusion2D.py:85, cov_advection_var_diffusion2D.py:85)
+            s += ", Λ = %2.2f" % (np.exp(p["w"][0]) if self.Hvar else p["w"][0])
         elif self.wkind is not None:
             h = p["w"].size // 2
             s += ", wx = %2.2f" % np.mean(p["w"][:h]) + ", wy = %2.2f" % np.mean(p["w"][h:])
         if self.timed:
             s += ", σ = %2.2f" % np.exp(p["sigma"])
-        s += ", τ = %2.2f" % np.exp(par[-1])
+        s += (", τ = %2.2f" if self.timed else ",τ = %2.2f") % np.exp(par[-1])       # (sic, whittle_matern2D.py print)
         if self.timed and par.size > self.n_own + 1:
             s += "\n Q0: " + self.mod0.print(par[self.n_own:])[:-10]
         return s

@@ -329,6 +329,16 @@ class SeperableSpatialTemporalHa2D(SeperableSpatialTemporal2D):
                 + ", vx = %2.2f" % ((par[18:27]).mean()) + ", vy = %2.2f" % ((par[27:36]).mean())
                 + ", a = %2.2f" % (par[36]) + ", σ = %2.2f" % (np.exp(par[37])) + ", τ = %2.2f" % (np.exp(par[38])))
 
+    def transDiff(self, par=None):
+        """``seperable_spatial_temporal_ha2D.py:36-45`` (the constant-coefficient form on the first four entries)."""
+        par = self.getPars() if par is None else np.asarray(par, dtype="float64")
+        aV = np.sqrt(par[2] ** 2 + par[3] ** 2)
+        cosh_aV = (np.exp(aV) + np.exp(-aV)) / 2
+        sinh_aV = (np.exp(aV) - np.exp(-aV)) / 2
+        self.tgamma = np.exp(par[1]) * (cosh_aV - sinh_aV)
+        self.tvx = np.sqrt(np.exp(par[0]) * sinh_aV / aV * (par[2] + aV))
+        self.tvy = np.sqrt(np.exp(par[0]) * sinh_aV / aV * (-par[2] + aV))
+
     def makeQt(self, a, sigma, T=10, diff=0):
         from scipy import sparse
         return sparse.csc_matrix(_qt_dense(T, qt_coeffs_a(a, sigma, diff)))
@@ -353,9 +363,12 @@ class SeperableSpatialTemporalIDiffusion2D(SeperableSpatialTemporalHa2D):
         self.kappa, self.gamma = par[0:9], par[9:18]
         self.a, self.sigma, self.tau = par[18], par[19], par[20]
 
+    def transDiff(self, par=None):
+        raise AttributeError("SeperableSpatialTemporalIDiffusion2D has no transDiff (half-angle classes only)")
+
     def print(self, par):
         return ("| κ = %2.2f" % (np.exp(par[0:9]).mean()) + ", γ = %2.2f" % (np.exp(par[9:18]).mean())
-                + ", a = %2.2f" % (par[18]) + ", σ = %2.2f" % (np.exp(par[19])) + ", τ = %2.2f" % (np.exp(par[20])))
+                + ", a = %2.2f" % (par[18]) + ", σ\t = %2.2f" % (np.exp(par[19])) + ", τ = %2.2f" % (np.exp(par[20])))   # (sic)
 
 
 class _KronDQ:

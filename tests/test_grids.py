@@ -27,3 +27,26 @@ def test_assimilate_adv_constant_field():
     if inner is not None:
         assert np.array_equal(ww[inner], np.tile([2.0, -1.0, 2.0, -1.0], (30, 1)))
     assert np.array_equal(ww[0], np.zeros(4))          # outer corner of the extension
+
+
+def test_transdiff_matches_reference():
+    """``transDiff`` of the nine half-angle classes (host helper, no device work) against the unmodified reference,
+    per-class quirks included (which of par[0] / par[1] scales tvx, tvy; constant form in VarWhittleMaternHa2D)."""
+    import pytest
+    import spdepy_b200 as sp
+    T = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "grid", "transdiff.npz"))
+    names = sorted({k.split("|")[0] for k in T.files})
+    assert len(names) == 9
+    x, y, t = np.linspace(0, 3, 8), np.linspace(0, 2, 7), np.linspace(0, 1, 10)
+    for name in names:
+        timed = "whittle" not in name
+        g = sp.grid(x=x, y=y, t=t) if timed else sp.grid(x=x, y=y)
+        mod = sp.model(grid=g, spde=name, ha=True, bc=3).mod
+        assert mod.getPars().shape == T[name + "|par"].shape
+        mod.transDiff(T[name + "|par"])
+        for k in ("tgamma", "tvx", "tvy"):
+            got, ref = np.asarray(getattr(mod, k), dtype="float64"), T[name + "|" + k]
+            assert got.shape == ref.shape and np.array_equal(got, ref), (name, k)
+    ani = sp.model(grid=sp.grid(x=x, y=y), spde="whittle-matern", ha=False, anisotropic=True, bc=3).mod
+    with pytest.raises(AttributeError):
+        ani.transDiff()
