@@ -38,6 +38,17 @@ if __name__ == "__main__":
                     row["print"] = mod.print(par)
                 except Exception as e:      # a few print() bodies index past the vector
                     row["print"] = "ERR:" + type(e).__name__
+                # initFit's return value is the start vector of Model.fit (model.py:43-47)
+                n = g.n if timed else g.Ns
+                idx = np.arange(0, n, 3)
+                for fq in ((False, True) if timed and "seperable" not in name else (None,)):
+                    m2 = sp.model(grid=g, spde=name, ha=ha, anisotropic=ani, bc=bc).mod
+                    kw = {"idx": idx}
+                    if fq is not None:
+                        kw["fitQ0"] = fq
+                    if name.startswith("cov"):
+                        kw["ww"] = np.zeros((g.Ns, 4))
+                    row["x0_%s" % fq] = np.array(m2.initFit(np.ones((idx.size, 2)), **kw), dtype="float64").tolist()
                 rows.append(row)
     os.makedirs(OUT, exist_ok=True)
     with open(os.path.join(OUT, "surface.json"), "w") as f:
