@@ -183,7 +183,9 @@ class _RegularMesh:
         return base if idxs is None else base[np.asarray(idxs)]
 
     def addCov(self, cov, inter=True, scale=False) -> None:
-        self.inter, self.scale, self.cov = inter, scale, cov
+        self.inter, self.cov = inter, cov
+        if self.timed:
+            self.scale = scale      # the spatial mesh of the reference never stores it (spatial2D_regular_mesh.py:55-58): no scaling there
         self.setS()
 
     def addInt(self) -> None:

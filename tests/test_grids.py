@@ -50,3 +50,49 @@ def test_transdiff_matches_reference():
     ani = sp.model(grid=sp.grid(x=x, y=y), spde="whittle-matern", ha=False, anisotropic=True, bc=3).mod
     with pytest.raises(AttributeError):
         ani.transDiff()
+
+
+def test_grid_helpers_match_reference():
+    """Both mesh classes: selection matrices (plain, observation subset, with intercept, with a covariate -- the spatial
+    mesh of the reference ignores ``scale``), spline-field evaluations, index maps, volume matrices."""
+    from scipy import sparse
+    H = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "grid", "helpers.npz"))
+
+    def ref(key):
+        if key + "|data" in H.files:
+            return sparse.csc_matrix((H[key + "|data"], H[key + "|indices"], H[key + "|indptr"]), shape=tuple(H[key + "|shape"]))
+        return H[key]
+
+    def same(a, b):
+        if sparse.issparse(b):
+            a = sparse.csc_matrix(a)
+            return a.shape == b.shape and abs(a - b).max() == 0
+        a = np.asarray(a)
+        return a.shape == b.shape and np.array_equal(a, b)
+
+    for c, (M, N, T, ext) in enumerate(H["cases"]):
+        x, y = np.linspace(0, 3, M), np.linspace(0, 2, N)
+        t = None if T < 0 else np.linspace(0, 1, T)
+        e = None if ext < 0 else int(ext)
+        g = grid(x=x, y=y, t=t, extend=e)
+        k = "c%d|" % c
+        idx = H[k + "idx"]
+        p9 = np.random.default_rng(4).normal(size=9)
+        got = {"shape": np.array(g.shape), "S": g.getS(), "S_idx": g.getS(idx), "evalB": g.evalB(p9), "evalBH": g.evalBH(p9),
+               "Dv": g.Dv, "iDv": g.iDv, "h": np.array([g.hx, g.hy])}
+        if T > 0:
+            got["evalAdv"] = g.evalAdv(np.random.default_rng(5).normal(size=18))
+            got["getIdx"] = np.array([g.getIdx(np.array([1, 2, 1])), g.getIdx(np.array([1, 2, 1]), extend=False)])
+            got["dt"] = g.dt
+        else:
+            got["getIdx"] = np.array([g.getIdx(np.array([1, 2])), g.getIdx(np.array([1, 2]), extend=False)])
+        g.addCov(H[k + "cov"], scale=True)
+        got["S_cov"], got["S_cov_idx"] = g.getS(), g.getS(idx)
+        g2 = grid(x=x, y=y, t=t, extend=e)
+        g2.addInt()
+        got["S_int_idx"] = g2.getS(idx)
+        for name, v in got.items():
+            assert same(v, ref(k + name)), (c, name)
+        # obs_nodes (this package's device-side form of S) addresses exactly the unit entries of S
+        S = sparse.csc_matrix(ref(k + "S_idx"))
+        assert np.array_equal(S.tocsr().indices, grid(x=x, y=y, t=t, extend=e).obs_nodes(idx))
