@@ -5,9 +5,11 @@ call sites ``advection_diffusion2D.py:117,193``, ``model.py:79,125``), a system 
 from ``/root/reference`` and from this image.  This module restates CHOLMOD's published supernodal
 algorithm (Chen, Davis, Hager, Rajamanickam, ACM TOMS 35(3), 2008: supernodal ``L L^T`` with dense
 ``potrf / trsm / syrk`` on the supernodes) in multifrontal form with NumPy / LAPACK dense kernels.
-The fill-reducing permutation and the supernode partition are taken from the build's own symbolic
-analysis (``spde_plan_perm`` / ``spde_plan_supernodes``, host code), because ``P^T L^-T z`` samples
-are only comparable under the same ``P`` (SURVEY.md finding 3).
+The fill-reducing permutation and the supernode partition come from a symbolic plan object (``n``,
+``perm``, ``supernodes()``): the tests pass the build's own analysis (``spde_plan_perm`` /
+``spde_plan_supernodes``, host code), because ``P^T L^-T z`` samples are only comparable under the same
+``P`` (SURVEY.md finding 3); ``bench.py --impl reference`` passes ``oracle/symbolic_oracle.OracleSymbolic``
+(nested dissection + CHOLMOD's published symbolic phase restated in C), so that arm never loads the product.
 
 It is used (a) as the independent numeric check of the CUDA factorisation at sizes where a dense
 factor is too big, and (b) as the CPU baseline that ``bench.py`` times on the GPU box's host cores.
@@ -20,6 +22,8 @@ import numpy as np
 from scipy import linalg as sla
 from scipy import sparse
 
+import symbolic_oracle as syo
+
 
 class SupernodalFactor:
     """``L L^T = P A P^T``; same method surface as ``sksparse.cholmod.Factor`` as used by the
@@ -27,7 +31,8 @@ class SupernodalFactor:
 
     def __init__(self, A, perm=None, plan=None):
         if plan is None:
-            raise ValueError("SupernodalFactor needs the build's symbolic plan (PlanHandle)")
+            raise ValueError("SupernodalFactor needs a symbolic plan: the build's PlanHandle (tests: samples under the "
+                             "same P) or oracle/symbolic_oracle.OracleSymbolic (bench.py's reference arm)")
         A = sparse.csc_matrix(A)
         n = A.shape[0]
         self.n = n
@@ -52,33 +57,39 @@ class SupernodalFactor:
         for s in range(ns):
             if parent[s] >= 0:
                 kids[parent[s]].append(s)
+        dpotrf, dtrsm, dsyrk = sla.lapack.dpotrf, sla.blas.dtrsm, sla.blas.dsyrk
         for s in range(ns):
             f, l = int(first[s]), int(first[s + 1])
             nc = l - f
             below = self.rows[rowptr[s]:rowptr[s + 1]]
             nr = below.size
-            m = nc + nr
-            F = np.zeros((m, m))
+            # the frontal matrix in three column-major blocks; only lower triangles are ever read
+            F11 = np.zeros((nc, nc), order="F")
+            F21 = np.zeros((nr, nc), order="F")
+            F22 = np.zeros((nr, nr), order="F") if nr else None
             # original entries of the pivot columns
             lo_p, hi_p = indptr[f], indptr[l]
             ri = indices[lo_p:hi_p]
             cj = np.repeat(np.arange(nc), np.diff(indptr[f:l + 1]))
-            pos = np.where(ri < l, ri - f, nc + np.searchsorted(below, ri))
-            F[pos, cj] = data[lo_p:hi_p]
-            # extend-add of the children's update matrices
+            piv = ri < l
+            F11[ri[piv] - f, cj[piv]] = data[lo_p:hi_p][piv]
+            if nr:
+                F21[np.searchsorted(below, ri[~piv]), cj[~piv]] = data[lo_p:hi_p][~piv]
+            # extend-add of the children's update matrices (their row lists are ascending, so the entries that land
+            # in the pivot block come first)
             for c_ in kids[s]:
                 cb = self.rows[rowptr[c_]:rowptr[c_ + 1]]
                 rel = np.where(cb < l, cb - f, nc + np.searchsorted(below, cb))
-                F[np.ix_(rel, rel)] += upd[c_]
+                syo.extend_add(upd[c_], rel, nc, F11, F21 if nr else None, F22)
                 upd[c_] = None
-            L11 = np.linalg.cholesky(F[:nc, :nc] + np.tril(F[:nc, :nc], -1).T)
+            L11, info = dpotrf(F11, lower=1, overwrite_a=1, clean=1)
+            if info != 0:
+                raise np.linalg.LinAlgError("matrix is not positive definite (pivot %d of the permuted matrix)" % (f + info - 1))
             self.L11[s] = L11
             if nr:
-                L21 = sla.solve_triangular(L11, F[nc:, :nc].T, lower=True).T
+                L21 = dtrsm(1.0, L11, F21, side=1, lower=1, trans_a=1, overwrite_b=1)
                 self.L21[s] = L21
-                U = F[nc:, nc:]
-                U = U + np.tril(U, -1).T
-                upd[s] = U - L21 @ L21.T
+                upd[s] = dsyrk(-1.0, L21, beta=1.0, c=F22, lower=1, overwrite_c=1)
             else:
                 self.L21[s] = np.zeros((0, nc))
 
@@ -97,35 +108,44 @@ class SupernodalFactor:
         out[self.perm] = x
         return out
 
+    # The right-hand sides are kept node-major ((n, k), C order): the rows of one supernode are then a contiguous
+    # (nc x k) block whose transpose is a column-major (k x nc) matrix, so the triangular solves and the updates run in
+    # place through BLAS dtrsm / dgemm "from the right" (Y^T L^T = B^T) without copies or finiteness scans.  Every dense
+    # call goes through scipy.linalg.blas -- mixing it with numpy's matmul would alternate between two OpenBLAS pools
+    # whose spinning workers fight for the cores.
     def solve_L(self, b, use_LDLt_decomposition=False):
-        x = np.array(b, dtype=np.float64)
+        x = np.array(b, dtype=np.float64, order="C")
         one = x.ndim == 1
         x = x.reshape(self.n, -1)
+        dtrsm, dgemm = sla.blas.dtrsm, sla.blas.dgemm
         for s in range(self.first.size - 1):
             f, l = int(self.first[s]), int(self.first[s + 1])
-            y = sla.solve_triangular(self.L11[s], x[f:l], lower=True)
-            x[f:l] = y
+            xt = x[f:l].T                                   # (k x nc), column-major view
+            dtrsm(1.0, self.L11[s], xt, side=1, lower=1, trans_a=1, overwrite_b=1)
             if self.L21[s].shape[0]:
                 below = self.rows[self.rowptr[s]:self.rowptr[s + 1]]
-                x[below] -= self.L21[s] @ y
+                x[below] -= dgemm(1.0, xt, self.L21[s], trans_b=1).T      # (L21 y)^T = y^T L21^T
         return x[:, 0] if one else x
 
     def solve_Lt(self, b, use_LDLt_decomposition=False):
-        x = np.array(b, dtype=np.float64)
+        x = np.array(b, dtype=np.float64, order="C")
         one = x.ndim == 1
         x = x.reshape(self.n, -1)
+        dtrsm, dgemm = sla.blas.dtrsm, sla.blas.dgemm
         for s in range(self.first.size - 2, -1, -1):
             f, l = int(self.first[s]), int(self.first[s + 1])
-            y = x[f:l]
+            xt = x[f:l].T
             if self.L21[s].shape[0]:
                 below = self.rows[self.rowptr[s]:self.rowptr[s + 1]]
-                y = y - self.L21[s].T @ x[below]
-            x[f:l] = sla.solve_triangular(self.L11[s], y, lower=True, trans="T")
+                dgemm(-1.0, x[below].T, self.L21[s], beta=1.0, c=xt, overwrite_c=1)       # x_s^T -= x_below^T L21
+            dtrsm(1.0, self.L11[s], xt, side=1, lower=1, trans_a=0, overwrite_b=1)
         return x[:, 0] if one else x
 
     def solve_A(self, b):
         b = np.asarray(b.toarray() if sparse.issparse(b) else b, dtype=np.float64)
         return self.apply_Pt(self.solve_Lt(self.solve_L(b[self.perm])))
+
+    __call__ = solve_A
 
 
 def factor_with_plan(plan):

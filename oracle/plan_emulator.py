@@ -16,7 +16,7 @@ GF_LOWER, GF_BETA0, GF_NEG, GF_ATOMIC, GF_GATHER_A, GF_SCATTER_C, GF_MIRROR = (1
                                                                             1 << 13, 1 << 14, 1 << 15)
 LK_GEMM, LK_POTRF, LK_EXTADD, LK_ZERO, LK_GATHER, LK_WTW, LK_EXTRACT, LK_GEMV, LK_SYNC, LK_COPY = range(10)
 NB = 64
-CFG = {0: (128, 128), 1: (128, 64), 2: (64, 64)}
+CFG = {0: (128, 128), 1: (128, 64), 2: (64, 64), 3: (128, 64)}      # 3 = warp-specialised bulk-async kernel
 
 LAUNCH = np.dtype([("kind", "i4"), ("variant", "i4"), ("task0", "i8"), ("ntasks", "i4"), ("tile0", "i8"),
                    ("ntiles", "i4"), ("a0", "i8"), ("a1", "i8"), ("lane", "i4"), ("pad", "i4")], align=True)

@@ -103,9 +103,22 @@ class DenseFactor:
     __call__ = solve_A
 
 
+_sparse_impl = None
+
+
+def set_sparse_factor(impl) -> None:
+    """``impl(A) -> Factor`` used for matrices too large for the dense stand-in (n > 12000): the BASELINE-config
+    fixtures of ``oracle/make_golden_baseline.py`` pass ``cpu_cholesky.SupernodalFactor`` bound to an
+    ``OracleSymbolic`` plan.  ``None`` restores the dense-only behaviour."""
+    global _sparse_impl
+    _sparse_impl = impl
+
+
 def _cholesky(A, **kwargs):
     if sparse.issparse(A) and A.shape[0] > 12000:
-        raise RuntimeError("dense CHOLMOD stand-in limited to n <= 12000")
+        if _sparse_impl is None:
+            raise RuntimeError("dense CHOLMOD stand-in limited to n <= 12000 (see set_sparse_factor)")
+        return _sparse_impl(A)
     return DenseFactor(A)
 
 

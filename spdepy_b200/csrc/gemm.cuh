@@ -269,6 +269,252 @@ k_gemm_grouped(const GemmTask *__restrict__ tasks, const TileRef *__restrict__ t
 }
 
 // ---------------------------------------------------------------------------------------------
+// Warp-specialised variant for operands with the tile dimension contiguous (A(i,kk) at a + i + col(kk)*lda,
+// B(j,kk) at b + j + kk*ldb): every k-column of an operand tile is one contiguous run of doubles, so the tile is
+// staged by one warp with 32 1-D bulk-async copies (cp.async.bulk.shared::cluster.global, SASS UBLKCP) that complete
+// on an mbarrier per stage; the other warps only wait on that barrier, load fragments and issue DMMA, and hand the
+// stage back through a second mbarrier -- there is no CTA-wide barrier in the main loop.  The producer role rotates
+// over the eight warps (one k-tile each), so a CTA is 256 threads and two CTAs per SM leave 128 registers per thread.  Measured on B200
+// (tools/gemm_lab.cu, profiles/r2_gemm_lab.txt): 35.3 TFLOP/s on 8192^3 (cuBLAS DGEMM: 35.5; the cp.async ring above:
+// 32.5), 34.7 on the K = 512 panel shape (30.9), 35.0 on the 10000 x 10000 x 2401 update of the top fronts (31.6).
+//   * tile 128 x 64, eight consumer warps of 32 x 32 (4 x 2), k-tile 16, four stages (100 KB: two CTAs per SM, so the
+//     epilogue of one overlaps the main loop of the other);
+//   * fragments are fetched as double2 from two ADJACENT rows (columns), which feed two different 8x8 MMA tiles --
+//     rows 16p + 2*(lane/4) + {0,1} -- half the shared-memory load instructions for the same bytes; the +4 double
+//     column padding keeps these 16-byte loads bank-conflict free;
+//   * bulk copies move whole 16-byte units and cannot zero-fill: a tile with an odd row count reads one row more (the
+//     operand spaces have even leading dimensions, so the row exists; it only feeds rows / columns of C that are never
+//     written), and the k-columns beyond K of the last k-tile are masked in registers by the consumers.
+constexpr int WS_BM = 128, WS_BN = 64, WS_BK = 16, WS_STAGES = 4, WS_WARPS_M = 4, WS_WARPS_N = 2;
+constexpr int WS_CONSUMERS = WS_WARPS_M * WS_WARPS_N;
+constexpr int WS_THREADS = WS_CONSUMERS * 32;
+constexpr int WS_LDA = WS_BM + 4, WS_LDB = WS_BN + 4;
+constexpr int WS_STAGE_ELEMS = (WS_LDA + WS_LDB) * WS_BK;
+constexpr int gemm_ws_smem_bytes()
+{
+    constexpr int pipe = WS_STAGES * WS_STAGE_ELEMS * 8 + 2 * WS_STAGES * 8 + 16;
+    constexpr int epi = (WS_BM + 2) * WS_BN * 8;
+    return pipe > epi ? pipe : epi;
+}
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+template <int STG>
+__global__ void __launch_bounds__(WS_THREADS, 2)
+k_gemm_ws(const GemmTask *__restrict__ tasks, const TileRef *__restrict__ tiles, GemmSpaces sp)
+{
+    constexpr int BM = WS_BM, BN = WS_BN, BKT = WS_BK;
+    static_assert(STG == WS_STAGES, "shared-memory size is computed for WS_STAGES");
+    constexpr int WM = BM / WS_WARPS_M, WN = BN / WS_WARPS_N, MT = WM / 8, NTL = WN / 8;
+    static_assert(MT % 2 == 0 && NTL % 2 == 0, "paired fragment loads need an even number of 8x8 tiles per warp");
+    static_assert(BKT == 16, "the producer maps lanes 0-15 to the k-columns of A and lanes 16-31 to those of B");
+    constexpr int A_ELEMS = WS_LDA * BKT, B_ELEMS = WS_LDB * BKT;
+    extern __shared__ __align__(16) double smem[];
+    double *sA = smem, *sB = smem + STG * A_ELEMS;
+    unsigned long long *full = reinterpret_cast<unsigned long long *>(smem + STG * WS_STAGE_ELEMS);
+    unsigned long long *empty = full + STG;
+
+    pdl_enter();
+    const TileRef tr = tiles[blockIdx.x];
+    const GemmTask tk = tasks[tr.task];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int K = tk.K;
+    const int nk = (K + BKT - 1) / BKT;
+    if (tid == 0) {
+        for (int s = 0; s < STG; s++) { mbar_init(full + s, 1); mbar_init(empty + s, WS_CONSUMERS); }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+    // ---- producer state of this lane: lanes 0-15 copy k-column `lane` of A, lanes 16-31 k-column `lane-16` of B.
+    // The producer ROLE rotates over the warps (k-tile t is issued by warp (t - STG + 1) mod 8 at the top of its
+    // iteration t - STG + 1), so no warp -- and none of its registers -- is set aside for it.
+    const bool isB = lane >= 16;
+    const int pk = lane & 15;
+    const double *gsrc;
+    long long gstride;
+    unsigned pbytes, tile_bytes;
+    {
+        const int i0 = tr.ti * BM, j0 = tr.tj * BN;
+        const int rowsA = min(BM, tk.M - i0), rowsB = min(BN, tk.N - j0);
+        const unsigned bytesA = (unsigned)((rowsA + (rowsA & 1)) * 8), bytesB = (unsigned)((rowsB + (rowsB & 1)) * 8);
+        gsrc = isB ? sp.base[(tk.flags >> 3) & 7] + tk.b + j0 : sp.base[tk.flags & 7] + tk.a + i0;
+        gstride = isB ? tk.ldb : tk.lda;
+        pbytes = isB ? bytesB : bytesA;
+        tile_bytes = bytesA + bytesB;
+    }
+    const int *gather = (!isB && (tk.flags & GF_GATHER_A)) ? sp.idx + tk.aidx : nullptr;
+    double *pdst = (isB ? sB + pk * WS_LDB : sA + pk * WS_LDA);
+    auto produce = [&](int t) {
+        const int s = t % STG;
+        const int k0 = t * BKT, kv = min(BKT, K - k0);
+        if (lane == 0) mbar_expect_tx(full + s, tile_bytes * kv);
+        __syncwarp();
+        if (pk < kv) {
+            const long long col = gather ? (long long)gather[k0 + pk] : (long long)(k0 + pk);
+            bulk_g2s(pdst + s * (isB ? B_ELEMS : A_ELEMS), gsrc + col * gstride, pbytes, full + s);
+        }
+    };
+    if (warp == 0)
+        for (int t = 0; t < STG - 1 && t < nk; t++) produce(t);
+
+    const int wm = warp % WS_WARPS_M, wn = warp / WS_WARPS_M;
+    const int lr = lane >> 2, lc = lane & 3;
+    double acc[MT][NTL][2];
+#pragma unroll
+    for (int a = 0; a < MT; a++)
+#pragma unroll
+        for (int b = 0; b < NTL; b++) { acc[a][b][0] = 0.0; acc[a][b][1] = 0.0; }
+    {
+        const double *pA = sA + wm * WM + 2 * lr + lc * WS_LDA;
+        const double *pB = sB + wn * WN + 2 * lr + lc * WS_LDB;
+        for (int kt = 0; kt < nk; kt++) {
+            {   // stage k-tile kt + STG - 1 into the slot that k-tile kt - 1 occupied, once every warp has released it
+                const int pt = kt + STG - 1;
+                if (pt < nk && warp == (kt & (WS_CONSUMERS - 1))) {
+                    if (kt >= 1) mbar_wait(empty + (pt % STG), ((pt / STG) - 1) & 1);
+                    produce(pt);
+                }
+            }
+            const int s = kt % STG;
+            mbar_wait(full + s, (kt / STG) & 1);
+            const double *cA = pA + s * A_ELEMS;
+            const double *cB = pB + s * B_ELEMS;
+            const int kv = K - kt * BKT - lc;            // this lane's k index is valid while k4 < kv
+#pragma unroll
+            for (int k4 = 0; k4 < BKT; k4 += 4) {
+                double fa[MT], fb[NTL];
+#pragma unroll
+                for (int a = 0; a < MT; a += 2) {
+                    const double2 v = *reinterpret_cast<const double2 *>(cA + k4 * WS_LDA + a * 8);
+                    fa[a] = v.x; fa[a + 1] = v.y;
+                }
+#pragma unroll
+                for (int b = 0; b < NTL; b += 2) {
+                    const double2 v = *reinterpret_cast<const double2 *>(cB + k4 * WS_LDB + b * 8);
+                    fb[b] = v.x; fb[b + 1] = v.y;
+                }
+                if (k4 >= kv) {                          // k-columns beyond K were never copied: mask them
+#pragma unroll
+                    for (int a = 0; a < MT; a++) fa[a] = 0.0;
+#pragma unroll
+                    for (int b = 0; b < NTL; b++) fb[b] = 0.0;
+                }
+#pragma unroll
+                for (int a = 0; a < MT; a++)
+#pragma unroll
+                    for (int b = 0; b < NTL; b++) dmma884(acc[a][b][0], acc[a][b][1], fa[a], fb[b]);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty + s);
+        }
+    }
+    // ---- epilogue: accumulators -> shared memory -> coalesced 16-byte read-modify-write of C,
+    // same flag semantics as k_gemm_grouped
+    constexpr int LDS = BM + 2, NCT = WS_CONSUMERS * 32;
+    double *sC = smem;
+    __syncthreads();      // every warp is done with the operand stages
+    // (re-read through volatile pointers so that none of this is kept live across the main loop)
+    const volatile TileRef *vr = tiles + blockIdx.x;
+    const volatile GemmTask *vt = tasks + vr->task;
+    const int flags = vt->flags;
+    const int ei0 = vr->ti * BM, ej0 = vr->tj * BN;
+    const int erows = min(BM, vt->M - ei0), ecols = min(BN, vt->N - ej0);
+    const bool neg = flags & GF_NEG, beta0 = flags & GF_BETA0, lower = flags & GF_LOWER;
+    const bool atomic = flags & GF_ATOMIC, mirror = flags & GF_UPPER_MIRROR;
+#pragma unroll
+    for (int a = 0; a < MT; a++)
+#pragma unroll
+        for (int b = 0; b < NTL; b++)
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                // paired loads permute rows and columns inside blocks of 16: MMA tile a holds rows 16(a/2) + 2 lr + (a&1)
+                const int r = wm * WM + (a / 2) * 16 + 2 * lr + (a & 1);
+                const int c = wn * WN + (b / 2) * 16 + 2 * (lc * 2 + e) + (b & 1);
+                const double v = neg ? -acc[a][b][e] : acc[a][b][e];
+                sC[c * LDS + r] = v;
+            }
+    __syncthreads();
+    const int ldc = vt->ldc;
+    double *gC = sp.base[(flags >> 6) & 7] + vt->c;
+    const int *scat = (flags & GF_SCATTER_C) ? sp.idx + vt->cidx : nullptr;
+    constexpr int RP = BM / 2;
+    for (int id = tid; id < RP * BN; id += NCT) {
+        const int cl = id / RP, rl = (id % RP) * 2;
+        if (cl >= ecols || rl >= erows) continue;
+        const int r = ei0 + rl, c = ej0 + cl;
+        const bool two = rl + 1 < erows;
+        bool w0 = true, w1 = two;
+        if (lower) { w0 = r >= c; w1 = two && (r + 1 >= c); }
+        if (!w0 && !w1) continue;
+        const double v0 = sC[cl * LDS + rl], v1 = sC[cl * LDS + rl + 1];
+        const long long col = scat ? (long long)scat[c] : (long long)c;
+        double *p = gC + r + col * ldc;
+        if (atomic) {
+            if (w0) atomicAdd(p, v0);
+            if (w1) atomicAdd(p + 1, v1);
+        } else if (w0 && w1 && ((reinterpret_cast<uintptr_t>(p) & 15) == 0)) {
+            double2 o = beta0 ? make_double2(0.0, 0.0) : *reinterpret_cast<const double2 *>(p);
+            o.x += v0; o.y += v1;
+            *reinterpret_cast<double2 *>(p) = o;
+        } else {
+            if (w0) p[0] = beta0 ? v0 : p[0] + v0;
+            if (w1) p[1] = beta0 ? v1 : p[1] + v1;
+        }
+    }
+    if (mirror) {
+        double *gM = sp.base[(flags >> 6) & 7] + vt->c2;
+        constexpr int CP = BN / 2;
+        for (int id = tid; id < CP * BM; id += NCT) {
+            const int rl = id / CP, cl = (id % CP) * 2;
+            if (rl >= erows || cl >= ecols) continue;
+            const bool two = cl + 1 < ecols;
+            const double v0 = sC[cl * LDS + rl], v1 = two ? sC[(cl + 1) * LDS + rl] : 0.0;
+            double *q = gM + (ej0 + cl) + (long long)(ei0 + rl) * ldc;
+            if (atomic) {
+                atomicAdd(q, v0);
+                if (two) atomicAdd(q + 1, v1);
+            } else if (two && ((reinterpret_cast<uintptr_t>(q) & 15) == 0)) {
+                double2 o = beta0 ? make_double2(0.0, 0.0) : *reinterpret_cast<const double2 *>(q);
+                o.x += v0; o.y += v1;
+                *reinterpret_cast<double2 *>(q) = o;
+            } else {
+                q[0] = beta0 ? v0 : q[0] + v0;
+                if (two) q[1] = beta0 ? v1 : q[1] + v1;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Small-M variant (M <= 4 right-hand sides): the triangular solves for the conditional mean have one
 // column per data replicate, where a 64x64 tensor-core tile would waste 63/64 of its rows.  These
 // are HBM-bound matrix-vector products: every element of L is read exactly once, coalesced, and K is

@@ -390,7 +390,16 @@ static cudaError_t launch_gemm(const Launch &L, const Program &P, const GemmSpac
 #undef V
     // tuning-only tile shapes (NT layout), reachable through spde_gemm_single
     if (ak == 0 && bk == 0) {
-        if (cfg == 3) return launch_gemm_variant<128, 64, 2, 2, false, false>(L, P, sp, st);    // 4 warps, 64x32 warp tiles
+        if (cfg == 3) {     // warp-specialised bulk-async kernel (k_gemm_ws): the production kernel of the N/N layout
+            static bool ws_attr = false;
+            if (!ws_attr) {
+                cudaError_t e = cudaFuncSetAttribute(k_gemm_ws<WS_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_ws_smem_bytes());
+                if (e != cudaSuccess) return e;
+                ws_attr = true;
+            }
+            return launch_pdl(k_gemm_ws<WS_STAGES>, dim3(L.ntiles), dim3(WS_THREADS), (size_t)gemm_ws_smem_bytes(), st,
+                              P.d_gemm + L.task0, P.d_tiles + L.tile0, sp);
+        }
         if (cfg == 4) return launch_gemm_variant<128, 128, 4, 4, false, false>(L, P, sp, st);   // 16 warps, 32x32
         if (cfg == 5) return launch_gemm_variant<64, 128, 2, 4, false, false>(L, P, sp, st);    // 8 warps, 32x32
         if (cfg == 6) return launch_gemm_variant<128, 128, 4, 2, false, false>(L, P, sp, st);   // 8 warps, 32x64

@@ -14,8 +14,10 @@ namespace spde {
 
 static inline int up2(int x) { return x + (x & 1); }
 
-static constexpr int CFG_BM[3] = {128, 128, 64};
-static constexpr int CFG_BN[3] = {128, 64, 64};
+// tile shapes of the grouped GEMM configurations; 3 = the warp-specialised bulk-async kernel (N/N layout only)
+static constexpr int CFG_BM[4] = {128, 128, 64, 128};
+static constexpr int CFG_BN[4] = {128, 64, 64, 64};
+static constexpr int CFG_WS = 3;
 
 // tile configuration of a grouped launch: the largest tile that still gives >= 2 CTAs per SM
 static constexpr int kSMs = 148;
@@ -128,9 +130,14 @@ struct LevelBuilder {
             // four warps (3-4 resident CTAs per SM) matches or beats the larger tiles on every problem shape of the
             // schedules -- square, K = 512 panels and skinny N = 64 -- so it is used for all grouped launches
             // (k-tile 32 with a 2-stage ring: +1-2 % on full launches, +16 % on under-filled skinny ones).
+            // Operands with the tile dimension contiguous on both sides (the factorisation's updates, the Takahashi
+            // product, the forward substitution) go to the warp-specialised bulk-async kernel: 34-35 TFLOP/s where the
+            // cp.async ring gives 30-32 (tools/gemm_lab.cu, profiles/r2_gemm_lab.txt).  SPDE_GEMM_WS=0 disables it.
             const char *env = getenv("SPDE_TILE");
             cfg = env ? atoi(env) : 2;
             if (cfg < 0 || cfg > 2) cfg = 2;
+            const char *ws = getenv("SPDE_GEMM_WS");
+            if ((key & 3) == 0 && !(ws && atoi(ws) == 0)) cfg = CFG_WS;
         }
         const int variant = cfg * 4 + (key & 3);
         const int BM = CFG_BM[cfg], BN = CFG_BN[cfg];
@@ -432,7 +439,8 @@ static inline void selinv_node_steps(LevelBuilder &B, const SNode &x, int sp_z, 
         const int r0 = (p == x.nblk - 1) ? x.ncp : c0 + NB;
         const int mb = mrows - r0;
         const int64_t W = x.dinv + (int64_t)p * NB * NB;
-        const int ldy = up2(std::max(mb, 2));
+        // Y = L[below,p] W is kept TRANSPOSED (Yt: b x mb, leading dimension 64), which makes it an operand with the tile
+        // dimension contiguous in the product below (bulk-async kernel) -- a K-contiguous Y would be staged row by row
         // Z_pp = W^T W  (+ correction below)
         Step st;
         memset(&st, 0, sizeof st);
@@ -440,9 +448,9 @@ static inline void selinv_node_steps(LevelBuilder &B, const SNode &x, int sp_z, 
         st.w.w = W; st.w.dst = F + c0 + (int64_t)c0 * x.ld; st.w.ldd = x.ld; st.w.b = b; st.w.space = sp_z;
         q.push_back(st);
         if (mb <= 0) continue;
-        // Y = L[below,p] * W
-        B.add_gemm(q, B.task(SP_L, x.panel + r0 + (int64_t)c0 * x.ld, x.ld, SP_DINV, W, NB,
-                             SP_Y, Y, ldy, mb, b, b, GF_BETA0), false, true);
+        // Yt = W^T * L[below,p]^T   (A(i,kk) = W(kk,i): K contiguous;  B(j,kk) = L(r0+j, c0+kk): tile dimension contiguous)
+        B.add_gemm(q, B.task(SP_DINV, W, NB, SP_L, x.panel + r0 + (int64_t)c0 * x.ld, x.ld,
+                             SP_Y, Y, NB, b, mb, b, GF_BETA0), true, false);
         // Z[below,p] = -Z[below,below] * Y   (and its transpose into the row block)
         // Skinny product (N <= 64): for the big fronts near the root there are fewer row tiles than
         // SMs, so K is split into chunks that accumulate atomically into the (still zero) block.
@@ -458,21 +466,21 @@ static inline void selinv_node_steps(LevelBuilder &B, const SNode &x, int sp_z, 
         int clen = (mb + nchunk - 1) / nchunk;
         clen += clen & 1;
         for (int k0 = 0, ci = 0; k0 < mb; k0 += clen, ci++) {
-            GemmTask t = B.task(sp_z, F + r0 + (int64_t)(r0 + k0) * x.ld, x.ld, SP_Y, Y + k0, ldy,
+            GemmTask t = B.task(sp_z, F + r0 + (int64_t)(r0 + k0) * x.ld, x.ld, SP_Y, Y + (int64_t)k0 * NB, NB,
                                 sp_z, F + r0 + (int64_t)c0 * x.ld, x.ld, mb, b, std::min(clen, mb - k0),
                                 GF_NEG | GF_UPPER_MIRROR | (nchunk == 1 ? GF_BETA0 : GF_ATOMIC));
             t.c2 = F + c0 + (int64_t)r0 * x.ld;
-            if (ci == 0) B.add_gemm(q, t, false, true);
+            if (ci == 0) B.add_gemm(q, t, false, false);
             else B.join_gemm(q, t);
         }
         // Z_pp -= Y^T Z[below,p]   (split over K, accumulated atomically)
         const int chunk = 512;
         bool opened = false;
         for (int k0 = 0; k0 < mb; k0 += chunk) {
-            GemmTask u = B.task(SP_Y, Y + k0, ldy, sp_z, F + (r0 + k0) + (int64_t)c0 * x.ld, x.ld,
+            GemmTask u = B.task(SP_Y, Y + (int64_t)k0 * NB, NB, sp_z, F + (r0 + k0) + (int64_t)c0 * x.ld, x.ld,
                                 sp_z, F + c0 + (int64_t)c0 * x.ld, x.ld, b, b, std::min(chunk, mb - k0),
                                 GF_NEG | GF_ATOMIC);
-            if (!opened) { B.add_gemm(q, u, true, true, 2); opened = true; }
+            if (!opened) { B.add_gemm(q, u, false, true, 2); opened = true; }
             else B.join_gemm(q, u);
         }
     }

@@ -245,14 +245,16 @@ class Engine:
         st = self.plan.stats()
         return st["factor_bytes"] + st["arena_bytes"] + st["zarena_bytes"]
 
-    def use_streamed(self) -> bool:
+    def use_streamed(self, stores: int = 1) -> bool:
+        """``stores``: factor stores the caller needs resident at once (2 for the Hutchinson mode, which keeps the 3-D
+        factors of Q and of Q + tau S^T S; the update-matrix arenas and inverse fronts exist per store as well)."""
         env = os.environ.get("SPDE_STREAMED")
         if env is not None:
             return env not in ("0", "")
         if self.streamed is not None:
             return bool(self.streamed)
         total = torch.cuda.get_device_properties(torch.cuda.current_device()).total_memory
-        return self.incore_bytes() + 3 * 8 * self.nslots * self.n > 0.9 * total
+        return stores * self.incore_bytes() + 3 * 8 * self.nslots * self.n > 0.9 * total
 
     def ooc(self, backward: bool = True) -> _lib.OocHandle:
         """The streamed evaluator of this mesh (one at a time: its pool is most of the device).  The threshold that

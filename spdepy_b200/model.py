@@ -18,13 +18,23 @@ class Model:
         self.mod = None
         if spde is not None:
             self.model(spde=spde, grid=grid, parameters=parameters, ani=ani, ha=ha, bc=bc, mod0=mod0)
-        self.Q = None
+        self._Q = None
         self._Qdev = None
         self.Q_fac = None
         self.mvar = None
         self.mu = np.zeros(int(np.prod(self.grid.shape)))
         self.useCov = False
         self.sigmas = np.log(np.array([0.01, 140]))
+
+    # ``Q``: the precision as SciPy CSC, as in the reference (``model.py:123,132,152``).  After ``update`` /
+    # ``setModel(useCov=True)`` the matrix lives on the device and is exported on first read.
+    @property
+    def Q(self):
+        return self.getQ()
+
+    @Q.setter
+    def Q(self, value):
+        self._Q = value
 
     def setQ(self, par=None) -> None:
         self.mod.setQ(par=par)
@@ -37,7 +47,15 @@ class Model:
                              ani=ani, ha=ha, bc=bc)
         self.mod = spde_init(model=spde, grid=grid, parameters=parameters, ani=ani, ha=ha, bc=bc, mod0=mod0)
         self.spde_type = self.mod.type
-        self.optim = Optimize(self.mod.logLike)
+        self.optim = Optimize(self._objective)
+
+    def _objective(self, par):
+        """``mod.logLike`` as the optimiser calls it (``optim/__init__.py:44``).  Meshes evaluated by the streamed path
+        (posterior factor beyond device memory) have no Hutchinson mode -- it needs two resident 3-D factors -- so
+        they are fitted with the exact Takahashi gradient."""
+        if getattr(self.mod, "timed", False) and self.mod.engine.use_streamed():
+            return self.mod.logLike(par, exact_grad=True)
+        return self.mod.logLike(par)
 
     def fit(self, data, **kwargs):
         assert self.mod is not None
@@ -68,7 +86,7 @@ class Model:
         self._Qdev = self.mod._state["Q"].clone()
         self.tau = np.exp(self.mod.tau)
         self._border = None
-        if self.useCov:
+        if useCov:      # (the argument, not self.useCov: model.py:131)
             self.sigmas = sigmas if sigmas is not None else self.sigmas
             n = self.mod.engine.n
             if hasattr(self.sigmas, "__len__"):
@@ -131,15 +149,15 @@ class Model:
         self.mu = self.mu + tmp
 
     def getQ(self):
-        if self.Q is None and self._Qdev is not None:
+        if self._Q is None and self._Qdev is not None:
             Q11 = self.mod.engine.to_scipy(self._Qdev)
             if self.useCov and self._border is not None:
                 from scipy import sparse
                 B = sparse.csc_matrix(self._border.B.cpu().numpy())
                 Q11 = sparse.bmat([[Q11, B], [B.T, sparse.csc_matrix(self._border.C)]]).tocsc()
                 Q11.eliminate_zeros()
-            self.Q = Q11
-        return self.Q
+            self._Q = Q11
+        return self._Q
 
     # ------------------------------------------------------------------ bordered precision (useCov=True)
     def _cov_columns(self, idx=None):

@@ -154,7 +154,10 @@ class SPDE2D:
         if self.timed:
             self.sigma = float(p["sigma"])
             if par.size > self.n_own + 1:
-                self.mod0.setPars(par[self.n_own:])
+                # as the reference: the initial-field model is re-assembled with its block of the joint vector
+                # (mod0.setQ(par=par[7:]), advection_diffusion2D.py:46-47), so that later own-parameter calls
+                # (setQ(), logLike(..., fitQ0=False), Model.setModel) read the new Q0 and not a stale one
+                self.mod0.setQ(par=par[self.n_own:])
         self.tau = par[-1]
         if not self.timed:
             self.sigma = np.log(np.sqrt(1 / np.exp(self.tau)))
@@ -603,7 +606,7 @@ class SPDE2D:
         # time into 2-D problems, so only the posterior precision needs the 3-D factorisation.  The
         # Hutchinson estimator solves with Q itself and keeps the 3-D factor of the prior.
         collapsed = self.timed and self.collapse_prior and (exact_grad or not grad)
-        if eng.use_streamed():
+        if eng.use_streamed(stores=1 if collapsed else 2):
             if not collapsed:
                 raise NotImplementedError("meshes beyond device memory (streamed evaluation) need the time-collapsed prior: "
                                           "a space-time model with exact_grad=True or grad=False")
