@@ -271,10 +271,11 @@ k_gemm_grouped(const GemmTask *__restrict__ tasks, const TileRef *__restrict__ t
 // ---------------------------------------------------------------------------------------------
 // Warp-specialised variant for operands with the tile dimension contiguous (A(i,kk) at a + i + col(kk)*lda,
 // B(j,kk) at b + j + kk*ldb): every k-column of an operand tile is one contiguous run of doubles, so the tile is
-// staged by one warp with 32 1-D bulk-async copies (cp.async.bulk.shared::cluster.global, SASS UBLKCP) that complete
-// on an mbarrier per stage; the other warps only wait on that barrier, load fragments and issue DMMA, and hand the
-// stage back through a second mbarrier -- there is no CTA-wide barrier in the main loop.  The producer role rotates
-// over the eight warps (one k-tile each), so a CTA is 256 threads and two CTAs per SM leave 128 registers per thread.  Measured on B200
+// staged by ONE producer warp with 32 1-D bulk-async copies (cp.async.bulk.shared::cluster.global, SASS UBLKCP) that
+// complete on an mbarrier per stage, while WS_CONSUMERS warps do nothing but wait on that barrier, load fragments and
+// issue DMMA; a stage is handed back through a second mbarrier, so there is no CTA-wide barrier in the main loop.  (A
+// variant in which the producer role rotates over the consumer warps was measured 4-15 % slower: the issuing warp then
+// waits for the slowest consumer of the slot it refills.)  Measured on B200
 // (tools/gemm_lab.cu, profiles/r2_gemm_lab.txt): 35.3 TFLOP/s on 8192^3 (cuBLAS DGEMM: 35.5; the cp.async ring above:
 // 32.5), 34.7 on the K = 512 panel shape (30.9), 35.0 on the 10000 x 10000 x 2401 update of the top fronts (31.6).
 //   * tile 128 x 64, eight consumer warps of 32 x 32 (4 x 2), k-tile 16, four stages (100 KB: two CTAs per SM, so the
@@ -287,7 +288,7 @@ k_gemm_grouped(const GemmTask *__restrict__ tasks, const TileRef *__restrict__ t
 //     written), and the k-columns beyond K of the last k-tile are masked in registers by the consumers.
 constexpr int WS_BM = 128, WS_BN = 64, WS_BK = 16, WS_STAGES = 4, WS_WARPS_M = 4, WS_WARPS_N = 2;
 constexpr int WS_CONSUMERS = WS_WARPS_M * WS_WARPS_N;
-constexpr int WS_THREADS = WS_CONSUMERS * 32;
+constexpr int WS_THREADS = (WS_CONSUMERS + 1) * 32;
 constexpr int WS_LDA = WS_BM + 4, WS_LDB = WS_BN + 4;
 constexpr int WS_STAGE_ELEMS = (WS_LDA + WS_LDB) * WS_BK;
 constexpr int gemm_ws_smem_bytes()
@@ -329,7 +330,7 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned by
 }
 
 template <int STG>
-__global__ void __launch_bounds__(WS_THREADS, 2)
+__global__ void __launch_bounds__(WS_THREADS)
 k_gemm_ws(const GemmTask *__restrict__ tasks, const TileRef *__restrict__ tiles, GemmSpaces sp)
 {
     constexpr int BM = WS_BM, BN = WS_BN, BKT = WS_BK;
@@ -344,48 +345,44 @@ k_gemm_ws(const GemmTask *__restrict__ tasks, const TileRef *__restrict__ tiles,
     unsigned long long *empty = full + STG;
 
     pdl_enter();
-    const TileRef tr = tiles[blockIdx.x];
-    const GemmTask tk = tasks[tr.task];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int K = tk.K;
-    const int nk = (K + BKT - 1) / BKT;
     if (tid == 0) {
         for (int s = 0; s < STG; s++) { mbar_init(full + s, 1); mbar_init(empty + s, WS_CONSUMERS); }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     __syncthreads();
-    // ---- producer state of this lane: lanes 0-15 copy k-column `lane` of A, lanes 16-31 k-column `lane-16` of B.
-    // The producer ROLE rotates over the warps (k-tile t is issued by warp (t - STG + 1) mod 8 at the top of its
-    // iteration t - STG + 1), so no warp -- and none of its registers -- is set aside for it.
-    const bool isB = lane >= 16;
-    const int pk = lane & 15;
-    const double *gsrc;
-    long long gstride;
-    unsigned pbytes, tile_bytes;
-    {
+    if (warp == WS_CONSUMERS) {
+        // ---- producer warp: lanes 0-15 copy k-column `lane` of A, lanes 16-31 k-column `lane - 16` of B, one bulk copy each
+        const TileRef tr = tiles[blockIdx.x];
+        const GemmTask tk = tasks[tr.task];
         const int i0 = tr.ti * BM, j0 = tr.tj * BN;
         const int rowsA = min(BM, tk.M - i0), rowsB = min(BN, tk.N - j0);
         const unsigned bytesA = (unsigned)((rowsA + (rowsA & 1)) * 8), bytesB = (unsigned)((rowsB + (rowsB & 1)) * 8);
-        gsrc = isB ? sp.base[(tk.flags >> 3) & 7] + tk.b + j0 : sp.base[tk.flags & 7] + tk.a + i0;
-        gstride = isB ? tk.ldb : tk.lda;
-        pbytes = isB ? bytesB : bytesA;
-        tile_bytes = bytesA + bytesB;
-    }
-    const int *gather = (!isB && (tk.flags & GF_GATHER_A)) ? sp.idx + tk.aidx : nullptr;
-    double *pdst = (isB ? sB + pk * WS_LDB : sA + pk * WS_LDA);
-    auto produce = [&](int t) {
-        const int s = t % STG;
-        const int k0 = t * BKT, kv = min(BKT, K - k0);
-        if (lane == 0) mbar_expect_tx(full + s, tile_bytes * kv);
-        __syncwarp();
-        if (pk < kv) {
-            const long long col = gather ? (long long)gather[k0 + pk] : (long long)(k0 + pk);
-            bulk_g2s(pdst + s * (isB ? B_ELEMS : A_ELEMS), gsrc + col * gstride, pbytes, full + s);
+        const bool isB = lane >= 16;
+        const int pk = lane & 15;
+        const double *gsrc = isB ? sp.base[(tk.flags >> 3) & 7] + tk.b + j0 : sp.base[tk.flags & 7] + tk.a + i0;
+        const long long gstride = isB ? tk.ldb : tk.lda;
+        const unsigned pbytes = isB ? bytesB : bytesA;
+        const int *gather = (!isB && (tk.flags & GF_GATHER_A)) ? sp.idx + tk.aidx : nullptr;
+        double *pdst = isB ? sB + pk * WS_LDB : sA + pk * WS_LDA;
+        const int pstage = isB ? B_ELEMS : A_ELEMS;
+        const int nk = (tk.K + BKT - 1) / BKT;
+        for (int kt = 0; kt < nk; kt++) {
+            const int s = kt % STG;
+            if (kt >= STG) mbar_wait(empty + s, ((kt / STG) - 1) & 1);
+            const int k0 = kt * BKT, kv = min(BKT, tk.K - k0);
+            if (lane == 0) mbar_expect_tx(full + s, (bytesA + bytesB) * kv);
+            __syncwarp();
+            if (pk < kv) {
+                const long long col = gather ? (long long)gather[k0 + pk] : (long long)(k0 + pk);
+                bulk_g2s(pdst + s * pstage, gsrc + col * gstride, pbytes, full + s);
+            }
         }
-    };
-    if (warp == 0)
-        for (int t = 0; t < STG - 1 && t < nk; t++) produce(t);
-
+        return;
+    }
+    // ---- consumer warps.  Only K is read from the task before the main loop: everything the epilogue needs is read
+    // afterwards, which keeps the loop (64 accumulator registers + fragments) inside the 96-register budget of two
+    // resident CTAs per SM.
     const int wm = warp % WS_WARPS_M, wn = warp / WS_WARPS_M;
     const int lr = lane >> 2, lc = lane & 3;
     double acc[MT][NTL][2];
@@ -394,16 +391,11 @@ k_gemm_ws(const GemmTask *__restrict__ tasks, const TileRef *__restrict__ tiles,
 #pragma unroll
         for (int b = 0; b < NTL; b++) { acc[a][b][0] = 0.0; acc[a][b][1] = 0.0; }
     {
+        const int K = tasks[tiles[blockIdx.x].task].K;
+        const int nk = (K + BKT - 1) / BKT;
         const double *pA = sA + wm * WM + 2 * lr + lc * WS_LDA;
         const double *pB = sB + wn * WN + 2 * lr + lc * WS_LDB;
         for (int kt = 0; kt < nk; kt++) {
-            {   // stage k-tile kt + STG - 1 into the slot that k-tile kt - 1 occupied, once every warp has released it
-                const int pt = kt + STG - 1;
-                if (pt < nk && warp == (kt & (WS_CONSUMERS - 1))) {
-                    if (kt >= 1) mbar_wait(empty + (pt % STG), ((pt / STG) - 1) & 1);
-                    produce(pt);
-                }
-            }
             const int s = kt % STG;
             mbar_wait(full + s, (kt / STG) & 1);
             const double *cA = pA + s * A_ELEMS;
@@ -441,7 +433,7 @@ k_gemm_ws(const GemmTask *__restrict__ tasks, const TileRef *__restrict__ tiles,
     // same flag semantics as k_gemm_grouped
     constexpr int LDS = BM + 2, NCT = WS_CONSUMERS * 32;
     double *sC = smem;
-    __syncthreads();      // every warp is done with the operand stages
+    asm volatile("bar.sync 1, %0;\n" ::"n"(NCT) : "memory");      // every consumer is done with the operand stages
     // (re-read through volatile pointers so that none of this is kept live across the main loop)
     const volatile TileRef *vr = tiles + blockIdx.x;
     const volatile GemmTask *vt = tasks + vr->task;
@@ -462,7 +454,7 @@ k_gemm_ws(const GemmTask *__restrict__ tasks, const TileRef *__restrict__ tiles,
                 const double v = neg ? -acc[a][b][e] : acc[a][b][e];
                 sC[c * LDS + r] = v;
             }
-    __syncthreads();
+    asm volatile("bar.sync 1, %0;\n" ::"n"(NCT) : "memory");
     const int ldc = vt->ldc;
     double *gC = sp.base[(flags >> 6) & 7] + vt->c;
     const int *scat = (flags & GF_SCATTER_C) ? sp.idx + vt->cidx : nullptr;

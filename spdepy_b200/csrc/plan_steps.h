@@ -137,7 +137,14 @@ struct LevelBuilder {
             cfg = env ? atoi(env) : 2;
             if (cfg < 0 || cfg > 2) cfg = 2;
             const char *ws = getenv("SPDE_GEMM_WS");
-            if ((key & 3) == 0 && !(ws && atoi(ws) == 0)) cfg = CFG_WS;
+            if ((key & 3) == 0 && !(ws && atoi(ws) == 0)) {
+                // ... unless the launch has fewer 128x64 tiles than SMs: such launches are latency-bound, and the 64x64 ring
+                // kernel (twice the CTAs, shorter prologue) is 10-15 % quicker there (profiles/r2_ws_sweep.txt)
+                long long nt = 0;
+                for (const Step *st : steps)
+                    for (int g = st->g0; g < st->g0 + st->gn && nt < kSMs; g++) nt += count_tiles(pool[g], CFG_WS);
+                if (nt >= kSMs) cfg = CFG_WS;
+            }
         }
         const int variant = cfg * 4 + (key & 3);
         const int BM = CFG_BM[cfg], BN = CFG_BN[cfg];

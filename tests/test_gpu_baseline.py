@@ -132,10 +132,12 @@ def test_c2_against_reference(bc):
     assert abs(m.last["logdetQ"] - float(d["logdetQ"])) <= 1e-9 * abs(float(d["logdetQ"]))
     assert abs(m.last["logdetQc"] - float(d["logdetQc"])) <= 1e-9 * abs(float(d["logdetQc"]))
     assert m.logLike(par, grad=False) == pytest.approx(float(d["like_nograd"]), rel=1e-9)
-    # exact gradient: same likelihood; every component within the Monte-Carlo scatter of the 100-probe estimate
+    # exact gradient: same likelihood; every component within the Monte-Carlo scatter of the 100-probe estimate (per-
+    # component SD 1e-4 ... 2e-3 at nh1 = 100; the exact traces themselves are pinned against the
+    # oracle's dense-inverse formula in test_gpu_loglike.py and against finite differences in test_gpu_fullsize.py)
     like_e, jac_e = m.logLike(par, grad=True, exact_grad=True)
     assert abs(like_e - float(d["like"])) <= 1e-9 * abs(float(d["like"]))
-    assert np.all(np.abs(jac_e - d["jac"]) <= 0.35 * np.abs(d["jac"]) + 2e-3), (jac_e, d["jac"])
+    assert np.all(np.abs(jac_e - d["jac"]) <= 1e-2), (jac_e, d["jac"])
     # samples with identical draws under the build's permutation: oracle supernodal Cholesky on the build's plan
     m.setQ(par)
     mod.setModel()
