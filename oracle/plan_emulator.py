@@ -200,6 +200,12 @@ class Emulator:
     def _wtw(self, P, L):
         for t in P.wtw[L["task0"]:L["task0"] + L["ntasks"]]:
             b = int(t["b"])
+            if int(t["pad"]) == 1:      # copy mode: the 64x64 inverses of an outer block onto the block diagonal of Wf
+                for j in range((b + NB - 1) // NB):
+                    bj = min(NB, b - j * NB)
+                    Wj = self.sp[3][int(t["w"]) + j * NB * NB:int(t["w"]) + (j + 1) * NB * NB].reshape(NB, NB, order="F")[:bj, :bj]
+                    self._view(int(t["space"]), int(t["dst"]) + j * NB * (int(t["ldd"]) + 1), int(t["ldd"]), bj, bj)[:, :] = Wj
+                continue
             W = self.sp[3][int(t["w"]):int(t["w"]) + NB * NB].reshape(NB, NB, order="F")[:b, :b]
             self._view(int(t["space"]), int(t["dst"]), int(t["ldd"]), b, b)[:, :] = W.T @ W
 
@@ -314,15 +320,17 @@ class OocEmulator(Emulator):
 
     def _copy(self, L):
         """LK_COPY: variant 0 parks pool[a0:a0+a1] at host offset task0 (only when a backward pass follows);
-        variant 1 is the point where slice a0 of the panel must have come back -- the interpreter fetches it exactly
-        there, so a step that reads a slice before its wait record sees the NaN poison."""
+        variant 1 is the point where slice a0 of the panel (and every later slice) must have come back -- the
+        interpreter fetches them exactly there, so a step that reads a slice before its wait record sees the NaN poison."""
         if int(L["variant"]) == 0:
             if self.hostbuf is not None:
                 a0, a1, h = int(L["a0"]), int(L["a1"]), int(L["task0"])
                 self.hostbuf[h:h + a1] = self.pool[a0:a0 + a1]
         else:
-            off, ln, h = (int(v) for v in self.chunks[int(L["a0"])])
-            self.pool[off:off + ln] = self.hostbuf[h:h + ln]
+            # (the slices come back last slice first on ONE stream: when slice a0 has arrived, so have all later ones)
+            for c in range(int(L["a0"]), len(self.chunks)):
+                off, ln, h = (int(v) for v in self.chunks[c])
+                self.pool[off:off + ln] = self.hostbuf[h:h + ln]
 
     def _scatter_factor(self, s, g, Qslots, cnt, tau):
         self.pool[g["off_L"]:g["off_L"] + g["l_size"]] = 0.0

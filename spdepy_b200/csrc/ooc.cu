@@ -113,6 +113,10 @@ void Ooc::segment(int64_t top_bytes)
         if (segs[i].parent_seg >= 0) segs[segs[i].parent_seg].kids.push_back((int)i);
     // local layout of every segment (offsets relative to the segment's regions, made absolute by plan_memory)
     osn = p.sn;
+    // two-level Takahashi recursion: the outer-block inverses of a front live behind its Yt scratch in the Y region
+    const char *envt = getenv("SPDE_SELINV_OUTER");
+    const bool sel_outer = envt ? atoi(envt) != 0 : true;
+    yoff_of.assign(osn.size(), 0);
     for (OocSeg &g : segs) {
         const int nd = g.dmax - g.dmin + 1;
         std::vector<int64_t> upd_used(nd, 0), front_used(nd, 0), y_used(nd, 0);
@@ -128,7 +132,15 @@ void Ooc::segment(int64_t top_bytes)
             upd_used[d] += (int64_t)x.ldu * x.nr;
             x.front = front_used[d];
             front_used[d] += (int64_t)x.ld * x.ld;
-            y_used[d] += (int64_t)x.ld * NB;
+            yoff_of[s] = y_used[d];
+            if (sel_outer && x.nblk > 1) {
+                x.winv = y_used[d] + ybuf_need(x);
+                y_used[d] += ybuf_need(x) + winv_size(x);
+                y_used[d] += y_used[d] & 1;
+            } else {
+                x.winv = -1;
+                y_used[d] += (int64_t)x.ld * NB;
+            }
         }
         for (int d = 0; d < nd; d++) {
             const int par = (d + g.dmin) & 1;
@@ -222,6 +234,8 @@ void Ooc::build_tables()
             x.dinv += g.off_dinv;
             x.upd += g.off_ar[x.depth & 1];
             x.front += g.off_z[x.depth & 1];
+            yoff_of[s] += g.off_y;
+            if (x.winv >= 0) x.winv += g.off_y;
         }
     diagpos.resize(n);
     for (int j = 0; j < n; j++) {
@@ -302,6 +316,7 @@ void Ooc::build_programs()
     const int splitk_min = env_int("SPDE_SPLITK_MIN", 2048, 8);
     const char *envk = getenv("SPDE_SELINV_KCHUNK");
     const int kchunk = envk ? atoi(envk) : 1024;
+    const int kchunk2 = env_int("SPDE_SELINV_KCHUNK2", 0, 0);
     int max_nr = 2;
     for (const SNode &x : osn) max_nr = std::max(max_nr, x.nr);
     ident_base = 2 * (int64_t)S.rows.size();
@@ -394,21 +409,48 @@ void Ooc::build_programs()
                     L.ntiles = (int)(P.tiles.size() - L.tile0);
                     if (L.ntiles) P.launches.push_back(L);
                 }
+                // seeds of the diagonal blocks: W^T W of the single-block fronts and the outer-block inverses Wf / Wf^T Wf of
+                // the others are hoisted in front of the level's recursion -- except for a front whose panel is still
+                // arriving from the host, which builds them outer block by outer block behind the wait records
+                {
+                    int64_t yend = g.off_y;
+                    for (int s : lev) yend = std::max(yend, yoff_of[s] + (osn[s].winv >= 0 ? ybuf_need(osn[s]) + winv_size(osn[s]) : (int64_t)osn[s].ld * NB));
+                    bool any_multi = false;
+                    for (int s : lev) any_multi |= osn[s].winv >= 0;
+                    if (any_multi) zero_launch(P, SP_Y, g.off_y, yend);      // (the inverses are lower triangular: upper blocks stay zero)
+                }
+                if (!g.overlap) {
+                    std::vector<const SNode *> single, multi;
+                    std::vector<int64_t> ymulti;
+                    for (int s : lev) {
+                        if (osn[s].winv >= 0) { multi.push_back(&osn[s]); ymulti.push_back(yoff_of[s]); }
+                        else single.push_back(&osn[s]);
+                    }
+                    wtw_level_launch(P, single, sp_z);
+                    if (!multi.empty()) winv_level_launches(P, multi, ymulti, sp_z);
+                }
                 LevelBuilder B(P);
-                int64_t yoff = g.off_y;
                 for (int s : lev) {
                     std::vector<Step> q;
-                    if (g.overlap) {
+                    const SNode &x = osn[s];
+                    const int nblk = x.nblk;
+                    if (g.overlap && x.winv >= 0) {
+                        // outer blocks are visited last to first; the panel comes back in slices of OUTER block columns, last
+                        // slice first on one stream: the slice holding the first column of the outer block is the last one it needs
+                        selinv_node_steps_outer(B, x, sp_z, yoff_of[s], kchunk2, q, [&](std::vector<Step> &qq, int k) {
+                            qq.push_back(copy_step(1, (k * SEL_OUTER) / OUTER, 0, 0));
+                        }, true);
+                    } else if (g.overlap) {
                         // block columns are visited last to first: wait for slice c just before its last block column
-                        const int nblk = osn[s].nblk;
-                        selinv_node_steps(B, osn[s], sp_z, yoff, splitk_min, kchunk, q, [&](std::vector<Step> &qq, int pb) {
+                        selinv_node_steps(B, x, sp_z, yoff_of[s], splitk_min, kchunk, q, [&](std::vector<Step> &qq, int pb) {
                             const int c = pb / OUTER;
                             if (pb == std::min((c + 1) * OUTER, nblk) - 1) qq.push_back(copy_step(1, c, 0, 0));
                         });
+                    } else if (x.winv >= 0) {
+                        selinv_node_steps_outer(B, x, sp_z, yoff_of[s], kchunk2, q);
                     } else {
-                        selinv_node_steps(B, osn[s], sp_z, yoff, splitk_min, kchunk, q);
+                        selinv_node_steps(B, x, sp_z, yoff_of[s], splitk_min, kchunk, q, true);
                     }
-                    yoff += (int64_t)osn[s].ld * NB;
                     B.seq.push_back(std::move(q));
                 }
                 B.flush();

@@ -55,6 +55,7 @@ struct Ooc {
     Plan *plan = nullptr;
     std::vector<SNode> osn;                   // node records with absolute pool offsets
     std::vector<int> seg_of;                  // supernode -> segment
+    std::vector<int64_t> yoff_of;             // supernode -> its scratch in the Y region (Yt, then the outer-block inverses)
     std::vector<OocSeg> segs;
     std::vector<int> order;                   // forward processing order (backward = reverse)
     int64_t pool_size = 0, peak_fwd = 0, peak_bwd = 0, host_size = 0, stage_bytes = 0;

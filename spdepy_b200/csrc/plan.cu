@@ -303,9 +303,18 @@ __global__ void __launch_bounds__(256) k_wtw(const WtwTask *__restrict__ tasks, 
     __shared__ double w[NB][NB + 1];
     pdl_enter();
     const WtwTask t = tasks[blockIdx.x];
+    double *dst = sp.base[t.space] + t.dst;
+    if (t.pad == 1) {      // copy mode: the inverses W_j of the 64-column blocks of an outer block onto the block diagonal of Wf
+        const int nbl = (t.b + NB - 1) / NB;
+        for (int e = threadIdx.x; e < nbl * NB * NB; e += 256) {
+            const int j = e / (NB * NB), r = e % (NB * NB), i = r % NB, c = r / NB;
+            const int bj = min(NB, t.b - j * NB);
+            if (i < bj && c < bj) dst[(j * NB + i) + (long long)(j * NB + c) * t.ldd] = dinv[t.w + e];
+        }
+        return;
+    }
     for (int e = threadIdx.x; e < NB * NB; e += 256) w[e % NB][e / NB] = dinv[t.w + e];
     __syncthreads();
-    double *dst = sp.base[t.space] + t.dst;
     // thread = (row i, group of 16 columns): 16 independent accumulators, so the FP64 pipe latency (~40 cycles per
     // dependent FMA) is hidden instead of serialised along each dot product.  W is lower triangular with explicit
     // zeros above the diagonal, so k starts at i.
@@ -740,6 +749,8 @@ static int ensure_device(Plan &p, int which)
             if (p.arena_size[a]) SPDE_CUDA_CHECK(cudaMalloc((void **)&p.d_arena[which][a], p.arena_size[a] * sizeof(double)));
         SPDE_CUDA_CHECK(cudaMalloc((void **)&p.d_L[which], std::max<int64_t>(p.l_size, 2) * sizeof(double)));
         SPDE_CUDA_CHECK(cudaMalloc((void **)&p.d_dinv[which], std::max<int64_t>(p.dinv_size, 2) * sizeof(double)));
+        // (the outer-block inverses behind the 64x64 blocks are lower triangular: their upper blocks are never written)
+        SPDE_CUDA_CHECK(cudaMemset(p.d_dinv[which], 0, std::max<int64_t>(p.dinv_size, 2) * sizeof(double)));
     }
     return SPDE_OK;
 }

@@ -21,6 +21,8 @@ struct SNode {
     int64_t upd;       // offset of the nr x nr update matrix inside arena[depth & 1]
     int64_t front;     // offset of the ld x ld selected-inverse front inside zarena[depth & 1]
     int64_t rows;      // offset into the device index array of the structure rows
+    int64_t winv;      // offset (inverse-block store) of the full inverses of the 512-column outer diagonal blocks
+                       // used by the Takahashi recursion of fronts with more than one 64-column block; -1 = none
 };
 
 struct PotrfTask { long long blk; long long dinv; int ld, b, col0, pad; };

@@ -38,9 +38,21 @@ void Plan::build_layout()
         upd_used[x.depth] += (int64_t)x.ldu * x.nr;
         x.front = front_used[x.depth];
         front_used[x.depth] += (int64_t)x.ld * x.ld;
-        y_used[x.depth] += (int64_t)x.ld * NB;
         x.rows = S.rowptr[s];
+        x.winv = -1;
         by_depth[x.depth].push_back(s);
+    }
+    // full inverses of the outer diagonal blocks (two-level Takahashi recursion), behind the 64x64 inverses
+    const char *envt = getenv("SPDE_SELINV_OUTER");      // 0: the 64-column recursion everywhere (validation)
+    const bool sel_outer = envt ? atoi(envt) != 0 : true;
+    for (int s = 0; s < ns; s++) {
+        SNode &x = sn[s];
+        if (sel_outer && x.nblk > 1) {
+            x.winv = dinv_size;
+            dinv_size += winv_size(x);
+            dinv_size += dinv_size & 1;
+        }
+        y_used[x.depth] += x.winv >= 0 ? ybuf_need(x) : (int64_t)x.ld * NB;
     }
     arena_size[0] = arena_size[1] = zarena_size[0] = zarena_size[1] = 0;
     ybuf_size = 0;
@@ -126,12 +138,26 @@ void Plan::build_factor_program()
     const bool lookahead = envl ? atoi(envl) != 0 : false;
     const char *envo = getenv("SPDE_FACTOR_OUTER");     // test hook: small outer blocks exercise the look-ahead on small meshes
     const int OUTER = envo ? std::max(1, atoi(envo)) : spde::OUTER;
+    // The update-matrix arena of level d-1 is the arena the extend-add of level d has just consumed, so it is zeroed on the
+    // side lane under the (compute-bound) factorisation of level d instead of in front of level d-1: LK_SYNC records fork
+    // and join the lane; executors without lanes run the list in order, which is just as valid.
+    const bool zero_ahead = !lookahead && env_int("SPDE_ZERO_AHEAD", 1, 0) != 0;
+    auto sync = [&](int variant, int ev) {
+        Launch L;
+        memset(&L, 0, sizeof L);
+        L.kind = LK_SYNC; L.variant = variant; L.a0 = ev;
+        P.launches.push_back(L);
+    };
+    auto arena_used = [&](int d) {
+        int64_t used = 0;
+        for (int s : by_depth[d]) used = std::max(used, sn[s].upd + (int64_t)sn[s].ldu * sn[s].nr);
+        return used;
+    };
     for (int d = S.maxdepth; d >= 0; d--) {
         const std::vector<int> &lev = by_depth[d];
         const int sp_u = SP_AR0 + (d & 1), sp_child = SP_AR0 + ((d + 1) & 1);
-        int64_t used = 0;
-        for (int s : lev) used = std::max(used, sn[s].upd + (int64_t)sn[s].ldu * sn[s].nr);
-        zero_launch(P, sp_u, 0, used);
+        if (!zero_ahead || d == S.maxdepth) zero_launch(P, sp_u, 0, arena_used(d));
+        else if (arena_used(d) > 0) sync(2, d & 1);
         // extend-add, one round per child rank (deterministic summation order)
         size_t maxk = 0;
         for (int s : lev) maxk = std::max(maxk, kids[s].size());
@@ -163,6 +189,12 @@ void Plan::build_factor_program()
             L.ntiles = (int)(P.tiles.size() - L.tile0);
             if (L.ntiles) P.launches.push_back(L);
         }
+        if (zero_ahead && d > 0 && arena_used(d - 1) > 0) {
+            sync(0, 0);
+            zero_launch(P, sp_child, 0, arena_used(d - 1));
+            P.launches.back().lane = 1;
+            sync(1, (d - 1) & 1);
+        }
         // dense partial Cholesky of every front of the level
         int maxblk = 0;
         for (int s : lev) maxblk = std::max(maxblk, sn[s].nblk);
@@ -174,12 +206,6 @@ void Plan::build_factor_program()
             //   main: [wait far(O-2)]  near(O-1): block O-1 -> the columns of block O;   panel(O)
             //   bulk: [after panel(O)]  far(O): block O -> the columns beyond block O+1;  U -= L21[:,O] L21[:,O]^T
             // near(O-1) and far(O-2) write the same columns, hence the wait; everything else is disjoint.
-            auto sync = [&](int variant, int ev) {
-                Launch L;
-                memset(&L, 0, sizeof L);
-                L.kind = LK_SYNC; L.variant = variant; L.a0 = ev;
-                P.launches.push_back(L);
-            };
             const int maxO = (maxblk + OUTER - 1) / OUTER;
             for (int O = 0; O < maxO; O++) {
                 const int P0 = O * OUTER;
@@ -324,12 +350,26 @@ void Plan::build_selinv_program()
     const int splitk_min = env ? std::max(8, atoi(env)) : 2048;
     const char *envk = getenv("SPDE_SELINV_KCHUNK");
     const int kchunk = envk ? atoi(envk) : 1024;    // measured on C3 (tools/kchunk_sweep.sh): none 786 ms, 1024 781, 512 792, 256 830
+    const int kchunk2 = env_int("SPDE_SELINV_KCHUNK2", 0, 0);      // K chunk of the 512-column products of the two-level recursion
+    // (the inverse fronts of level d+1 go where those of level d-1 were, last read by the gather of level d: zeroed on
+    // the side lane under the recursion of level d, as the update-matrix arenas of the factorisation)
+    const bool zero_ahead = env_int("SPDE_ZERO_AHEAD", 1, 0) != 0;
+    auto sync = [&](int variant, int ev) {
+        Launch L;
+        memset(&L, 0, sizeof L);
+        L.kind = LK_SYNC; L.variant = variant; L.a0 = ev;
+        P.launches.push_back(L);
+    };
+    auto zarena_used = [&](int d) {
+        int64_t used = 0;
+        for (int s : by_depth[d]) used = std::max(used, sn[s].front + (int64_t)sn[s].ld * sn[s].ld);
+        return used;
+    };
     for (int d = 0; d <= S.maxdepth; d++) {
         const std::vector<int> &lev = by_depth[d];
         const int sp_z = SP_Z0 + (d & 1), sp_par = SP_Z0 + ((d + 1) & 1);
-        int64_t used = 0;
-        for (int s : lev) used = std::max(used, sn[s].front + (int64_t)sn[s].ld * sn[s].ld);
-        zero_launch(P, sp_z, 0, used);
+        if (!zero_ahead || d == 0) zero_launch(P, sp_z, 0, zarena_used(d));
+        else sync(2, d & 1);
         // Z_II of every front <- parent's front
         {
             Launch L;
@@ -357,12 +397,33 @@ void Plan::build_selinv_program()
             L.ntiles = (int)(P.tiles.size() - L.tile0);
             if (L.ntiles) P.launches.push_back(L);
         }
+        if (zero_ahead && d < S.maxdepth) {
+            sync(0, 0);
+            zero_launch(P, sp_par, 0, zarena_used(d + 1));
+            P.launches.back().lane = 1;
+            sync(1, (d + 1) & 1);
+        }
+        // seeds of the diagonal blocks, hoisted: W^T W of the single-block fronts in one launch, the outer-block
+        // inverses Wf and Wf^T Wf of the others in seven grouped launches
+        std::vector<int64_t> yoffs;
+        {
+            std::vector<const SNode *> single, multi;
+            std::vector<int64_t> ymulti;
+            int64_t yoff = 0;
+            for (int s : lev) {
+                yoffs.push_back(yoff);
+                if (sn[s].winv >= 0) { multi.push_back(&sn[s]); ymulti.push_back(yoff); yoff += ybuf_need(sn[s]); }
+                else { single.push_back(&sn[s]); yoff += (int64_t)sn[s].ld * NB; }
+            }
+            wtw_level_launch(P, single, sp_z);
+            if (!multi.empty()) winv_level_launches(P, multi, ymulti, sp_z);
+        }
         LevelBuilder B(P);
-        int64_t yoff = 0;
-        for (int s : lev) {
+        for (size_t i = 0; i < lev.size(); i++) {
+            const SNode &x = sn[lev[i]];
             std::vector<Step> q;
-            selinv_node_steps(B, sn[s], sp_z, yoff, splitk_min, kchunk, q);
-            yoff += (int64_t)sn[s].ld * NB;
+            if (x.winv >= 0) selinv_node_steps_outer(B, x, sp_z, yoffs[i], kchunk2, q);
+            else selinv_node_steps(B, x, sp_z, yoffs[i], splitk_min, kchunk, q, true);
             B.seq.push_back(std::move(q));
         }
         B.flush();

@@ -13,6 +13,11 @@
 namespace spde {
 
 static inline int up2(int x) { return x + (x & 1); }
+static inline int env_int(const char *name, int dflt, int lo)
+{
+    const char *e = getenv(name);
+    return e ? std::max(lo, atoi(e)) : dflt;
+}
 
 // tile shapes of the grouped GEMM configurations; 3 = the warp-specialised bulk-async kernel (N/N layout only)
 static constexpr int CFG_BM[4] = {128, 128, 64, 128};
@@ -434,9 +439,32 @@ static inline void bsolve_node_steps(LevelBuilder &B, const SNode &x, int k, int
 // Takahashi recursion on one front whose trailing block Z[below,below] is in place: block columns from last to
 // first.  Y = scratch of ld x 64 doubles at offset Y of the Y space.
 // `before_block(q, p)` (optional) is called before the first step that reads block column p of the factor.
+// One launch with the W^T W seeds of the diagonal blocks Z_pp of ALL block columns of the given fronts: they depend
+// on nothing but the inverse diagonal blocks, and Z_pp is first read (by its own correction) at step p, so the whole
+// level's seeds are hoisted in front of the recursion instead of one small launch per step.
+static inline void wtw_level_launch(Program &P, const std::vector<const SNode *> &nodes, int sp_z)
+{
+    Launch L;
+    memset(&L, 0, sizeof L);
+    L.kind = LK_WTW;
+    L.task0 = (int64_t)P.wtw.size();
+    for (const SNode *x : nodes)
+        for (int p = 0; p < x->nblk; p++) {
+            const int c0 = p * NB;
+            WtwTask w;
+            memset(&w, 0, sizeof w);
+            w.w = x->dinv + (int64_t)p * NB * NB;
+            w.dst = x->front + c0 + (int64_t)c0 * x->ld;
+            w.ldd = x->ld; w.b = std::min(NB, x->nc - c0); w.space = sp_z;
+            P.wtw.push_back(w);
+        }
+    L.ntasks = (int)(P.wtw.size() - L.task0);
+    if (L.ntasks > 0) P.launches.push_back(L);
+}
+
 template <class Hook>
 static inline void selinv_node_steps(LevelBuilder &B, const SNode &x, int sp_z, int64_t Y, int splitk_min, int kchunk,
-                                     std::vector<Step> &q, Hook before_block)
+                                     std::vector<Step> &q, Hook before_block, bool wtw_hoisted = false)
 {
     const int mrows = x.ncp + x.nr;
     const int64_t F = x.front;
@@ -453,7 +481,7 @@ static inline void selinv_node_steps(LevelBuilder &B, const SNode &x, int sp_z, 
         memset(&st, 0, sizeof st);
         st.kind = LK_WTW;
         st.w.w = W; st.w.dst = F + c0 + (int64_t)c0 * x.ld; st.w.ldd = x.ld; st.w.b = b; st.w.space = sp_z;
-        q.push_back(st);
+        if (!wtw_hoisted) q.push_back(st);
         if (mb <= 0) continue;
         // Yt = W^T * L[below,p]^T   (A(i,kk) = W(kk,i): K contiguous;  B(j,kk) = L(r0+j, c0+kk): tile dimension contiguous)
         B.add_gemm(q, B.task(SP_DINV, W, NB, SP_L, x.panel + r0 + (int64_t)c0 * x.ld, x.ld,
@@ -494,15 +522,195 @@ static inline void selinv_node_steps(LevelBuilder &B, const SNode &x, int sp_z, 
 }
 
 static inline void selinv_node_steps(LevelBuilder &B, const SNode &x, int sp_z, int64_t Y, int splitk_min, int kchunk,
-                                     std::vector<Step> &q)
+                                     std::vector<Step> &q, bool wtw_hoisted = false)
 {
-    selinv_node_steps(B, x, sp_z, Y, splitk_min, kchunk, q, [](std::vector<Step> &, int) {});
+    selinv_node_steps(B, x, sp_z, Y, splitk_min, kchunk, q, [](std::vector<Step> &, int) {}, wtw_hoisted);
 }
 
-static inline int env_int(const char *name, int dflt, int lo)
+// ---------------------------------------------------------------------------------------------
+// Two-level Takahashi recursion (fronts with more than one 64-column block, in-core schedules).
+// The pivot columns are walked in OUTER blocks O of SEL_OUTER*64 = 512 columns, last to first.  With
+// Wf = L_OO^-1 (the full inverse of the outer diagonal block, built by recursive doubling from the 64x64
+// inverses the factorisation leaves in the inverse-block store) and B = the rows below O:
+//     Yt     = Wf^T L[B,O]^T                       (w x mb, one strip of 64 rows per task: Wf is lower triangular)
+//     Z[B,O] = -Z[B,B] Yt^T                        (mb x w, K = mb: the one big product, N = 512 instead of 64)
+//     Z[O,O] = Wf^T Wf - Yt Z[B,O]                 (w x w)
+// Same flops as the 64-column recursion (which spends 2 mb w^2 on the rows of O below each of its blocks), but the
+// trailing block Z[B,B] is read once per 512 columns instead of once per 64 (8x less DRAM traffic on the dominant
+// operand), the chain has 3 dependent launches per 512 columns instead of 24, and most products need no split-K atomics.
+static inline int sel_outer_blocks()      // 64-column blocks per outer block (SPDE_SELINV_OUTER_BLOCKS: test hook for small meshes)
 {
-    const char *e = getenv(name);
-    return e ? std::max(lo, atoi(e)) : dflt;
+    return std::min(64, env_int("SPDE_SELINV_OUTER_BLOCKS", 8, 1));
+}
+#define SEL_OUTER (spde::sel_outer_blocks())
+#define SEL_W (SEL_OUTER * NB)
+
+struct OuterBlk { int c0, w, ldw, nb; int64_t wf; };
+static inline int n_outer(const SNode &x) { return (x.nblk + SEL_OUTER - 1) / SEL_OUTER; }
+static inline OuterBlk outer_block(const SNode &x, int k)
+{
+    OuterBlk o;
+    o.c0 = k * SEL_W;
+    o.w = std::min(SEL_W, x.nc - o.c0);
+    o.ldw = up2(o.w);
+    o.nb = (o.w + NB - 1) / NB;
+    o.wf = x.winv + (int64_t)k * SEL_W * SEL_W;
+    return o;
+}
+static inline int64_t winv_size(const SNode &x)
+{
+    if (x.nblk <= 1) return 0;
+    const int no = n_outer(x);
+    const int wl = x.nc - (no - 1) * SEL_W;
+    return (int64_t)(no - 1) * SEL_W * SEL_W + (int64_t)up2(wl) * wl;
+}
+static inline int64_t ybuf_need(const SNode &x) { return (int64_t)x.ld * (x.nblk > 1 ? SEL_W : NB); }
+
+// Copy task of one outer block: the 64x64 inverses W_j of its blocks onto the block diagonal of Wf (k_wtw, mode 1).
+static inline WtwTask winv_copy_task(const SNode &x, int k)
+{
+    const OuterBlk o = outer_block(x, k);
+    WtwTask w;
+    memset(&w, 0, sizeof w);
+    w.w = x.dinv + (int64_t)k * SEL_OUTER * NB * NB;
+    w.dst = o.wf;
+    w.ldd = o.ldw; w.b = o.w; w.space = SP_DINV;
+    w.pad = 1;      // mode: plain copy of every W_j (not W^T W)
+    return w;
+}
+
+// Doubling rounds inv([[A,0],[B,C]]) = [[A^-1,0],[-C^-1 B A^-1, C^-1]] of two grouped products each for the outer blocks
+// k_lo..k_hi-1 of one front (block diagonal already copied), then the seeds Z[O,O] = Wf^T Wf.  `toff` = scratch in the Y
+// space (<= 128 doubles per pivot column of the blocks treated).
+static inline void winv_doubling_steps(LevelBuilder &B, const SNode &x, int k_lo, int k_hi, int64_t toff0, int sp_z, std::vector<Step> &q)
+{
+    for (int s = 1; s < SEL_OUTER; s *= 2) {
+        // phase 0: T = L[C,A] Wf[A,A]      phase 1: Wf[C,A] = -Wf[C,C] T
+        for (int phase = 0; phase < 2; phase++) {
+            bool opened = false;
+            int64_t toff = toff0;
+            for (int k = k_lo; k < k_hi; k++) {
+                const OuterBlk o = outer_block(x, k);
+                for (int a0 = 0; a0 + s < o.nb; a0 += 2 * s) {
+                    const int ra = a0 * NB, rc = (a0 + s) * NB;
+                    const int sa = s * NB, sc = std::min(o.w, (a0 + 2 * s) * NB) - rc;
+                    const int ldt = up2(sc);
+                    GemmTask t;
+                    if (phase == 0)
+                        t = B.task(SP_L, x.panel + (o.c0 + rc) + (int64_t)(o.c0 + ra) * x.ld, x.ld,
+                                   SP_DINV, o.wf + ra + (int64_t)ra * o.ldw, o.ldw,
+                                   SP_Y, toff, ldt, sc, sa, sa, GF_BETA0);
+                    else
+                        t = B.task(SP_DINV, o.wf + rc + (int64_t)rc * o.ldw, o.ldw,
+                                   SP_Y, toff, ldt,
+                                   SP_DINV, o.wf + rc + (int64_t)ra * o.ldw, o.ldw, sc, sa, sc, GF_NEG | GF_BETA0);
+                    toff += (int64_t)ldt * sa;
+                    if (!opened) { B.add_gemm(q, t, false, true); opened = true; }
+                    else B.join_gemm(q, t);
+                }
+            }
+        }
+    }
+    for (int k = k_lo; k < k_hi; k++) {
+        const OuterBlk o = outer_block(x, k);
+        GemmTask t = B.task(SP_DINV, o.wf, o.ldw, SP_DINV, o.wf, o.ldw,
+                            sp_z, x.front + o.c0 + (int64_t)o.c0 * x.ld, x.ld, o.w, o.w, o.w, GF_BETA0);
+        if (k == k_lo) B.add_gemm(q, t, true, true);
+        else B.join_gemm(q, t);
+    }
+}
+
+// Hoisted, once per level: Wf of every outer block of the given fronts and the seeds Z[O,O] = Wf^T Wf, in seven grouped
+// launches.  `yoff[i]` = scratch of front i in the Y space.
+static inline void winv_level_launches(Program &P, const std::vector<const SNode *> &nodes, const std::vector<int64_t> &yoff, int sp_z)
+{
+    {
+        Launch L;
+        memset(&L, 0, sizeof L);
+        L.kind = LK_WTW;
+        L.task0 = (int64_t)P.wtw.size();
+        for (const SNode *xp : nodes)
+            for (int k = 0; k < n_outer(*xp); k++) P.wtw.push_back(winv_copy_task(*xp, k));
+        L.ntasks = (int)(P.wtw.size() - L.task0);
+        if (L.ntasks > 0) P.launches.push_back(L);
+    }
+    LevelBuilder B(P);
+    for (size_t fi = 0; fi < nodes.size(); fi++) {
+        std::vector<Step> q;
+        winv_doubling_steps(B, *nodes[fi], 0, n_outer(*nodes[fi]), yoff[fi], sp_z, q);
+        B.seq.push_back(std::move(q));
+    }
+    B.flush();
+}
+
+// The recursion itself on one front (winv >= 0) whose trailing block Z[below,below] is in place and whose seeds are set.
+// `before_outer(q, k)` (optional) is called before the first step that reads outer block k of the factor; with
+// `inline_winv` the inverse Wf and the seed of an outer block are built right there, in front of its three products
+// (streamed evaluator: the panel arrives from the host outer block by outer block), instead of hoisted per level.
+template <class Hook>
+static inline void selinv_node_steps_outer(LevelBuilder &B, const SNode &x, int sp_z, int64_t Y, int kchunk, std::vector<Step> &q,
+                                           Hook before_outer, bool inline_winv)
+{
+    const int mrows = x.ncp + x.nr;
+    const int64_t F = x.front;
+    const int no = n_outer(x);
+    for (int k = no - 1; k >= 0; k--) {
+        const OuterBlk o = outer_block(x, k);
+        const int c0 = o.c0, w = o.w, ldY = o.ldw;
+        const int r0 = (k == no - 1) ? x.ncp : c0 + w;
+        const int mb = mrows - r0;
+        before_outer(q, k);
+        if (inline_winv) {
+            Step st;
+            memset(&st, 0, sizeof st);
+            st.kind = LK_WTW;
+            st.w = winv_copy_task(x, k);
+            q.push_back(st);
+            winv_doubling_steps(B, x, k, k + 1, Y, sp_z, q);
+        }
+        if (mb <= 0) continue;
+        // Yt = Wf^T L[B,O]^T, one task per strip of 64 rows (rows of strip i only see the blocks i.. of O)
+        for (int i = 0; i < o.nb; i++) {
+            const int bi = std::min(NB, w - i * NB);
+            GemmTask t = B.task(SP_DINV, o.wf + i * NB + (int64_t)i * NB * o.ldw, o.ldw,
+                                SP_L, x.panel + r0 + (int64_t)(c0 + i * NB) * x.ld, x.ld,
+                                SP_Y, Y + i * NB, ldY, bi, mb, w - i * NB, GF_BETA0);
+            if (i == 0) B.add_gemm(q, t, true, false);
+            else B.join_gemm(q, t);
+        }
+        // Z[B,O] = -Z[B,B] Yt^T (and its transpose into the row block).  K is cut into chunks (atomic accumulation into the
+        // zeroed block) when the launch would have too few tiles for the machine, and to bound the duration of one tile:
+        // a launch ends with a partially filled wave, and a 128x64 tile with K = mb in the thousands runs for a millisecond
+        const int tiles0 = ((mb + 127) / 128) * ((w + NB - 1) / NB);
+        int nchunk = 1;
+        if (tiles0 < 4 * kSMs) nchunk = std::max(1, std::min((4 * kSMs + tiles0 - 1) / tiles0, mb / 256));
+        if (kchunk > 0 && mb > kchunk + kchunk / 2) nchunk = std::max(nchunk, (mb + kchunk - 1) / kchunk);
+        int clen = (mb + nchunk - 1) / nchunk;
+        clen += clen & 1;
+        for (int k0 = 0, ci = 0; k0 < mb; k0 += clen, ci++) {
+            GemmTask t = B.task(sp_z, F + r0 + (int64_t)(r0 + k0) * x.ld, x.ld, SP_Y, Y + (int64_t)k0 * ldY, ldY,
+                                sp_z, F + r0 + (int64_t)c0 * x.ld, x.ld, mb, w, std::min(clen, mb - k0),
+                                GF_NEG | GF_UPPER_MIRROR | (nchunk == 1 ? GF_BETA0 : GF_ATOMIC));
+            t.c2 = F + c0 + (int64_t)r0 * x.ld;
+            if (ci == 0) B.add_gemm(q, t, false, false);
+            else B.join_gemm(q, t);
+        }
+        // Z[O,O] -= Yt Z[B,O]   (split over K, accumulated atomically onto the seed)
+        const int chunk = 512;
+        bool opened = false;
+        for (int k0 = 0; k0 < mb; k0 += chunk) {
+            GemmTask u = B.task(SP_Y, Y + (int64_t)k0 * ldY, ldY, sp_z, F + (r0 + k0) + (int64_t)c0 * x.ld, x.ld,
+                                sp_z, F + c0 + (int64_t)c0 * x.ld, x.ld, w, w, std::min(chunk, mb - k0),
+                                GF_NEG | GF_ATOMIC);
+            if (!opened) { B.add_gemm(q, u, false, true, 2); opened = true; }
+            else B.join_gemm(q, u);
+        }
+    }
+}
+
+static inline void selinv_node_steps_outer(LevelBuilder &B, const SNode &x, int sp_z, int64_t Y, int kchunk, std::vector<Step> &q)
+{
+    selinv_node_steps_outer(B, x, sp_z, Y, kchunk, q, [](std::vector<Step> &, int) {}, false);
 }
 
 }  // namespace spde

@@ -132,8 +132,9 @@ def _dense_case(M, N, T, bc, seed=1):
     return plan, pat, A, rng
 
 
-@pytest.mark.parametrize("outer,overlap,selinv", [(1, 1, True), (1, 1, False), (2, 1, True), (1, 0, True)])
-def test_streamed_panel_slices(monkeypatch, outer, overlap, selinv):
+@pytest.mark.parametrize("outer,overlap,selinv,selblocks", [(1, 1, True, 1), (1, 1, False, 1), (2, 1, True, 2), (1, 0, True, 1),
+                                                            (1, 1, True, 3), (2, 1, True, 1), (1, 1, True, 0)])
+def test_streamed_panel_slices(monkeypatch, outer, overlap, selinv, selblocks):
     """Overlapped panel traffic of the spilled top segments (LK_COPY records): with one 64-column block per outer block
     the fronts on top are parked in several slices during their factorisation and fetched back slice by slice, last
     slice first, by the wait records inside the Takahashi schedule; the interpreter fetches a slice only at its wait
@@ -141,6 +142,11 @@ def test_streamed_panel_slices(monkeypatch, outer, overlap, selinv):
     without the selected inverse (the solve waits for all slices) and with the overlap switched off."""
     monkeypatch.setenv("SPDE_FACTOR_OUTER", str(outer))
     monkeypatch.setenv("SPDE_OOC_OVERLAP", str(overlap))
+    # outer blocks of the two-level Takahashi recursion: as wide as the slices, wider, narrower; 0 = the 64-column recursion
+    if selblocks:
+        monkeypatch.setenv("SPDE_SELINV_OUTER_BLOCKS", str(selblocks))
+    else:
+        monkeypatch.setenv("SPDE_SELINV_OUTER", "0")
     plan, pat, A, rng = _dense_case(24, 22, 9, 3)
     n = plan.n
     ooc = _lib.OocHandle(plan, 150000)
@@ -153,7 +159,11 @@ def test_streamed_panel_slices(monkeypatch, outer, overlap, selinv):
                 park = ooc.export(s, 0, 0, pe.LAUNCH)
                 wait = ooc.export(s, 3, 0, pe.LAUNCH)
                 assert (park["kind"] == pe.LK_COPY).sum() == nsl[s] + 1          # slices + inverse diagonal blocks
-                assert ((wait["kind"] == pe.LK_COPY) & (wait["variant"] == 1)).sum() == nsl[s]
+                nwait = ((wait["kind"] == pe.LK_COPY) & (wait["variant"] == 1)).sum()
+                if selblocks in (0, outer):
+                    assert nwait == nsl[s]                  # one wait record per slice
+                else:
+                    assert 1 <= nwait                        # one per outer block of the recursion (several may name one slice)
     else:
         assert max(nsl) == 0
     em = pe.OocEmulator(plan, ooc)

@@ -140,9 +140,44 @@ def test_emulated_large_fronts(shape):
     assert np.abs(full[mask] - Zd[mask]).max() < 1e-10 * np.abs(Zd).max()
 
 
+@pytest.mark.parametrize("blocks,kchunk2", [("2", "0"), ("3", "96"), ("1", "2048")])
+def test_emulated_selinv_outer_blocks(monkeypatch, blocks, kchunk2):
+    """Two-level Takahashi recursion with several outer blocks per front (normally 512 columns wide): outer-block
+    inverses by recursive doubling (ragged last block, non-power-of-two block counts), unsplit and K-chunked products;
+    and the same mesh through the 64-column recursion (SPDE_SELINV_OUTER=0) gives the same selected inverse."""
+    monkeypatch.setenv("SPDE_SELINV_OUTER_BLOCKS", blocks)
+    monkeypatch.setenv("SPDE_SELINV_KCHUNK2", kchunk2)
+    M, N, T, bc = 24, 22, 9, 3
+    plan = _lib.PlanHandle(M, N, T, bc)
+    assert plan.info(13) > 64 * 2 * int(blocks)          # the widest front spans more than two outer blocks
+    pat = Pattern(M, N, T, bc)
+    n = plan.n
+    rng = np.random.default_rng(3)
+    W = pat.to_csc(rng.normal(size=pat.nslots * n))
+    A = (W + W.T) * 0.5
+    A = sparse.csc_matrix(A + sparse.diags(np.abs(A).sum(axis=1).A1 + 1.0))
+    em = pe.Emulator(plan)
+    assert em.factorize(pat.from_sparse(A)) == 0
+    prog = pe.Program(plan, 3)
+    assert (prog.wtw["pad"] == 1).any()                    # copy-mode tasks: the outer-block path is in use
+    Zq = em.selinv()
+    Zd = np.linalg.inv(A.toarray())
+    full = pat.to_csc(Zq).toarray()
+    mask = pat.to_csc(np.ones(pat.nslots * n)).toarray() != 0
+    assert np.abs(full[mask] - Zd[mask]).max() < 1e-10 * np.abs(Zd).max()
+    monkeypatch.setenv("SPDE_SELINV_OUTER", "0")
+    plan0 = _lib.PlanHandle(M, N, T, bc)
+    em0 = pe.Emulator(plan0)
+    assert em0.factorize(pat.from_sparse(A)) == 0
+    assert not (pe.Program(plan0, 3).wtw["pad"] == 1).any()
+    Z0 = em0.selinv()
+    assert np.abs(Z0 - Zq).max() < 1e-11 * np.abs(Zd).max()
+
+
 def test_emulated_selinv_split_k(monkeypatch):
     """The split-K variant of the skinny Takahashi product (normally only for fronts >= 2048 rows)."""
     monkeypatch.setenv("SPDE_SPLITK_MIN", "64")
+    monkeypatch.setenv("SPDE_SELINV_OUTER", "0")          # the 64-column recursion (what the streamed schedules use)
     M, N, T, bc = 20, 18, 6, 3
     plan = _lib.PlanHandle(M, N, T, bc)
     pat = Pattern(M, N, T, bc)
