@@ -731,20 +731,34 @@ def c5_block(args, m, inp, rank, world, local):
     gen = torch.Generator(device="cuda")
     blk = 512
 
+    marks = []        # (phase, event) pairs of the timed thetas: where the batch time goes (read after the final sync)
+
+    def mark(phase):
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        marks.append((phase, e))
+
     def one(theta, seed):
+        mark("start")
         like, jac = m.logLike(theta, grad=True, exact_grad=True)
+        mark("loglike_grad")
         # Model.sample at this theta (model.py:73-87): x = P^T L^-T z with L the factor of the 3-D prior
         eng.factorize(0, m._state["Q"])
+        mark("factor_prior")
         gen.manual_seed(8 + seed)
         for c0 in range(0, C5_SAMPLES, blk):
             z = torch.randn(eng.n, min(blk, C5_SAMPLES - c0), dtype=torch.float64, device="cuda", generator=gen)
+            mark("draws")
             x = eng.solve(0, z, 10)
             acc[npar + 1] += torch.linalg.vector_norm(x) ** 2        # device-side checksum, no host sync
+            mark("back_substitution")
         acc[0] += like
         acc[1:npar + 1] += torch.as_tensor(jac, device="cuda")
 
-    one(inp["theta"], 10 ** 6)          # warm-up: builds and captures the 512-column solve schedules
+    for w in range(2):                   # warm-up: the first call builds the 512-column solve schedules, the second captures their graphs
+        one(inp["theta"], 10 ** 6 + w)
     acc.zero_()
+    marks.clear()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -766,7 +780,12 @@ def c5_block(args, m, inp, rank, world, local):
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
         ms = float(tms.item())
     h = acc.cpu().numpy()
-    return {"workload": WORKLOADS["c5"][8], "thetas": C5_THETAS, "samples_per_theta": C5_SAMPLES, "n_gpus": world,
+    phase_ms = {}
+    for (_, e0), (ph, e1) in zip(marks[:-1], marks[1:]):
+        if ph != "start":
+            phase_ms[ph] = phase_ms.get(ph, 0.0) + e0.elapsed_time(e1)
+    phase_ms = {k: v / len(mine) for k, v in phase_ms.items()}
+    return {"workload": WORKLOADS["c5"][8], "phase_ms_per_theta_rank0": phase_ms, "thetas": C5_THETAS, "samples_per_theta": C5_SAMPLES, "n_gpus": world,
             "scaling": "strong", "value": C5_THETAS / (ms * 1e-3), "unit": "theta-evaluations/s (each with 1024 samples)",
             "ms_batch": ms, "ms_per_theta_per_gpu": ms / len(mine), "thetas_per_rank": len(mine),
             "sum_like": float(h[0]), "mean_sample_variance": float(h[npar + 1] / (eng.n * C5_SAMPLES * C5_THETAS)),

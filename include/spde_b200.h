@@ -143,6 +143,10 @@ int spde_factorize_async(spde_plan *p, int which, const double *d_Q, const doubl
 int spde_factor_wait(spde_plan *p, int which, void *stream);
 int spde_factor_info(spde_plan *p, int which, int *h_status, int *h_bad_column);
 int spde_logdet(spde_plan *p, int which, double *h_logdet, void *stream);
+/* The same value written to a DEVICE address, no copy and no synchronise (the scalars of one logLike evaluation are
+ * collected in one device vector and read back once; replaces the per-term NumPy scalars of
+ * advection_diffusion2D.py:198 and optim/__init__.py:44). */
+int spde_logdet_dev(spde_plan *p, int which, double *d_logdet, void *stream);
 
 /* ------------------------------------------------------------------ solves (K7) */
 /* X is n x k, ROW-major on the device (node-major: the k values of a node are contiguous); solved
@@ -197,6 +201,12 @@ int spde_q_apply(int M, int N, int T, int bc, const double *d_Q, const double *d
 int spde_dot(const double *d_X, const double *d_Y, int64_t len, double *h_out, void *stream);
 /* h_out[0] = sum_node w[node] * sum_p X[node,p]*Y[node,p] (X, Y row-major n x k). */
 int spde_wdot(const double *d_X, const double *d_Y, const double *d_w, int64_t n, int k, double *h_out, void *stream);
+/* Device-output forms of the three reductions (d_out[0] on the device, no copy, no synchronise): the likelihood and
+ * gradient scalars of one evaluation stay on the device until one read-back at the end (advection_diffusion2D.py:198-223). */
+int spde_dot_dev(const double *d_X, const double *d_Y, int64_t len, double *d_out, void *stream);
+int spde_wdot_dev(const double *d_X, const double *d_Y, const double *d_w, int64_t n, int k, double *d_out, void *stream);
+int spde_residual_ss_dev(const double *d_data, const double *d_mu, const int64_t *d_obs, int64_t nobs, int r,
+                         double *d_out, void *stream);
 /* h_out[0] = sum_{i,p} (data[i,p] - mu[obs[i],p])^2; data nobs x r, mu n x r, both row-major
  * (advection_diffusion2D.py:198). */
 int spde_residual_ss(const double *d_data, const double *d_mu, const int64_t *d_obs, int64_t nobs, int r,

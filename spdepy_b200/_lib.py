@@ -56,6 +56,7 @@ _SIGS = {
     "spde_factor_wait": (c_int, [c_vp, c_int, c_vp]),
     "spde_factor_info": (c_int, [c_vp, c_int, ctypes.POINTER(c_int), ctypes.POINTER(c_int)]),
     "spde_logdet": (c_int, [c_vp, c_int, ctypes.POINTER(c_dbl), c_vp]),
+    "spde_logdet_dev": (c_int, [c_vp, c_int, c_vp, c_vp]),
     "spde_solve": (c_int, [c_vp, c_int, c_int, c_vp, c_int, c_vp]),
     "spde_selinv": (c_int, [c_vp, c_int, c_vp, c_vp]),
     "spde_selinv_start": (c_int, [c_vp, c_int, c_vp]),
@@ -64,6 +65,9 @@ _SIGS = {
     "spde_dot": (c_int, [c_vp, c_vp, c_i64, ctypes.POINTER(c_dbl), c_vp]),
     "spde_wdot": (c_int, [c_vp, c_vp, c_vp, c_i64, c_int, ctypes.POINTER(c_dbl), c_vp]),
     "spde_residual_ss": (c_int, [c_vp, c_vp, c_vp, c_i64, c_int, ctypes.POINTER(c_dbl), c_vp]),
+    "spde_dot_dev": (c_int, [c_vp, c_vp, c_i64, c_vp, c_vp]),
+    "spde_wdot_dev": (c_int, [c_vp, c_vp, c_vp, c_i64, c_int, c_vp, c_vp]),
+    "spde_residual_ss_dev": (c_int, [c_vp, c_vp, c_vp, c_i64, c_int, c_vp, c_vp]),
     "spde_scatter_obs": (c_int, [c_vp, c_vp, c_i64, c_int, c_dbl, c_vp, c_vp]),
     "spde_add_diag": (c_int, [c_vp, c_vp, c_dbl, c_i64, c_vp]),
     "spde_sddmm": (c_int, [c_int, c_int, c_int, c_int, c_vp, c_vp, c_int, c_dbl, c_int, c_vp, c_vp]),

@@ -965,20 +965,31 @@ extern "C" int spde_factor_info(spde_plan *pp, int which, int *h_status, int *h_
     return SPDE_OK;
 }
 
-extern "C" int spde_logdet(spde_plan *pp, int which, double *h_logdet, void *stream)
+static int logdet_impl(spde_plan *pp, int which, double *out, bool device_out, void *stream)
 {
     Plan &p = *reinterpret_cast<Plan *>(pp);
     if (!p.factored[which]) { set_error("spde_logdet: not factorised"); return SPDE_ERR_ARG; }
     cudaStream_t st = (cudaStream_t)stream;
     { int rcj = join_store(p, which, st); if (rcj) return rcj; }
-    const int nb = 1024;
+    const int nb = std::max(1, std::min(1024, (p.sym.n + 1023) / 1024));
     count_launch(2);
     k_logdet_partial<<<nb, 256, 0, st>>>(p.d_L[which], p.d_diagpos, p.sym.n, p.d_red);
-    k_sum_final<<<1, 1024, 0, st>>>(p.d_red, nb, 2.0, p.d_red + nb);
+    k_sum_final<<<1, 1024, 0, st>>>(p.d_red, nb, 2.0, device_out ? out : p.d_red + nb);
     SPDE_LAUNCH_CHECK();
-    SPDE_CUDA_CHECK(cudaMemcpyAsync(h_logdet, p.d_red + nb, sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (device_out) return SPDE_OK;
+    SPDE_CUDA_CHECK(cudaMemcpyAsync(out, p.d_red + nb, sizeof(double), cudaMemcpyDeviceToHost, st));
     SPDE_CUDA_CHECK(cudaStreamSynchronize(st));
     return SPDE_OK;
+}
+extern "C" int spde_logdet(spde_plan *pp, int which, double *h_logdet, void *stream)
+{
+    return logdet_impl(pp, which, h_logdet, false, stream);
+}
+// same value written to a device address, without copy or synchronise (a NaN appears there when the factorisation
+// broke down; the status itself is still reported by spde_factor_wait / spde_factor_info)
+extern "C" int spde_logdet_dev(spde_plan *pp, int which, double *d_logdet, void *stream)
+{
+    return logdet_impl(pp, which, d_logdet, true, stream);
 }
 
 extern "C" int spde_solve(spde_plan *pp, int which, int mode, double *d_X, int k, void *stream)

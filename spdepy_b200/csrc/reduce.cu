@@ -304,18 +304,39 @@ extern "C" int spde_q_apply(int M, int N, int T, int bc, const double *d_Q, cons
     return SPDE_OK;
 }
 
-extern "C" int spde_dot(const double *d_X, const double *d_Y, int64_t len, double *h_out, void *stream)
+// second stage of a two-stage reduction: the sum of the nb partials goes to host memory (with a stream synchronise) or,
+// for the *_dev entry points, straight to a device address -- no copy, no synchronise: the likelihood / gradient
+// scalars of one evaluation are collected in one device vector and read back once
+static int finish_sum(double *out, bool device_out, cudaStream_t st, int nb)
+{
+    count_launch(2);
+    k_final<<<1, 1024, 0, st>>>(g_scratch, nb, device_out ? out : g_scratch + nb);
+    SPDE_LAUNCH_CHECK();
+    if (device_out) return SPDE_OK;
+    SPDE_CUDA_CHECK(cudaMemcpyAsync(out, g_scratch + nb, sizeof(double), cudaMemcpyDeviceToHost, st));
+    SPDE_CUDA_CHECK(cudaStreamSynchronize(st));
+    return SPDE_OK;
+}
+
+// grid of a streaming reduction: enough CTAs for the machine on long vectors, a handful on short ones (the 30x30 mesh)
+static inline int reduce_blocks(int64_t len) { return (int)std::max<int64_t>(1, std::min<int64_t>(1184, (len + 1023) / 1024)); }
+
+static int dot_impl(const double *d_X, const double *d_Y, int64_t len, double *out, bool device_out, void *stream)
 {
     int rc = ensure_scratch();
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    const int nb = 1184;   // 8 x 148
+    const int nb = reduce_blocks(len);
     k_dot_partial<<<nb, 256, 0, st>>>(d_X, d_Y, len, g_scratch);
-    k_final<<<1, 1024, 0, st>>>(g_scratch, nb, g_scratch + nb);
-    SPDE_LAUNCH_CHECK();
-    SPDE_CUDA_CHECK(cudaMemcpyAsync(h_out, g_scratch + nb, sizeof(double), cudaMemcpyDeviceToHost, st));
-    SPDE_CUDA_CHECK(cudaStreamSynchronize(st));
-    return SPDE_OK;
+    return finish_sum(out, device_out, st, nb);
+}
+extern "C" int spde_dot(const double *d_X, const double *d_Y, int64_t len, double *h_out, void *stream)
+{
+    return dot_impl(d_X, d_Y, len, h_out, false, stream);
+}
+extern "C" int spde_dot_dev(const double *d_X, const double *d_Y, int64_t len, double *d_out, void *stream)
+{
+    return dot_impl(d_X, d_Y, len, d_out, true, stream);
 }
 
 extern "C" int spde_sddmm(int M, int N, int T, int bc, const double *d_X, const double *d_Y, int k, double alpha,
@@ -391,34 +412,43 @@ extern "C" int spde_gemv_t(const double *d_B, const double *d_u, int rows, int c
     return SPDE_OK;
 }
 
-static int finish_sum(double *h_out, cudaStream_t st, int nb)
-{
-    k_final<<<1, 1024, 0, st>>>(g_scratch, nb, g_scratch + nb);
-    SPDE_LAUNCH_CHECK();
-    SPDE_CUDA_CHECK(cudaMemcpyAsync(h_out, g_scratch + nb, sizeof(double), cudaMemcpyDeviceToHost, st));
-    SPDE_CUDA_CHECK(cudaStreamSynchronize(st));
-    return SPDE_OK;
-}
-
-extern "C" int spde_wdot(const double *d_X, const double *d_Y, const double *d_w, int64_t n, int k, double *h_out, void *stream)
+static int wdot_impl(const double *d_X, const double *d_Y, const double *d_w, int64_t n, int k, double *out, bool device_out, void *stream)
 {
     int rc = ensure_scratch();
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    const int nb = 1184;
+    const int nb = reduce_blocks(n * k);
     k_wdot_partial<<<nb, 256, 0, st>>>(d_X, d_Y, d_w, n, k, g_scratch);
-    return finish_sum(h_out, st, nb);
+    return finish_sum(out, device_out, st, nb);
+}
+extern "C" int spde_wdot(const double *d_X, const double *d_Y, const double *d_w, int64_t n, int k, double *h_out, void *stream)
+{
+    return wdot_impl(d_X, d_Y, d_w, n, k, h_out, false, stream);
+}
+extern "C" int spde_wdot_dev(const double *d_X, const double *d_Y, const double *d_w, int64_t n, int k, double *d_out, void *stream)
+{
+    return wdot_impl(d_X, d_Y, d_w, n, k, d_out, true, stream);
 }
 
+static int resid_impl(const double *d_data, const double *d_mu, const int64_t *d_obs, int64_t nobs, int r, double *out, bool device_out,
+                      void *stream)
+{
+    int rc = ensure_scratch();
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nb = reduce_blocks(nobs * r);
+    k_resid_partial<<<nb, 256, 0, st>>>(d_data, d_mu, (const long long *)d_obs, nobs, r, g_scratch);
+    return finish_sum(out, device_out, st, nb);
+}
 extern "C" int spde_residual_ss(const double *d_data, const double *d_mu, const int64_t *d_obs, int64_t nobs, int r,
                                 double *h_out, void *stream)
 {
-    int rc = ensure_scratch();
-    if (rc) return rc;
-    cudaStream_t st = (cudaStream_t)stream;
-    const int nb = 1184;
-    k_resid_partial<<<nb, 256, 0, st>>>(d_data, d_mu, (const long long *)d_obs, nobs, r, g_scratch);
-    return finish_sum(h_out, st, nb);
+    return resid_impl(d_data, d_mu, d_obs, nobs, r, h_out, false, stream);
+}
+extern "C" int spde_residual_ss_dev(const double *d_data, const double *d_mu, const int64_t *d_obs, int64_t nobs, int r,
+                                    double *d_out, void *stream)
+{
+    return resid_impl(d_data, d_mu, d_obs, nobs, r, d_out, true, stream);
 }
 
 extern "C" int spde_scatter_obs(const double *d_data, const int64_t *d_obs, int64_t nobs, int r, double tau, double *d_b, void *stream)

@@ -50,6 +50,106 @@ def to_host(t: torch.Tensor) -> np.ndarray:
     return t.cpu().numpy()
 
 
+class Lazy:
+    """A scalar that lives in a :class:`ScalarPool` (or a linear expression of such scalars and host numbers): the
+    arithmetic of ``logLike`` is written as in the reference, but nothing is read from the device until the first
+    ``float()`` -- which fetches the whole pool in ONE device-to-host copy."""
+    __slots__ = ("pool", "fn")
+    __array_ufunc__ = None          # NumPy scalars defer to the reflected operators below
+
+    def __init__(self, pool, fn):
+        self.pool, self.fn = pool, fn
+
+    def __float__(self):
+        return float(self.fn(self.pool.fetch()))
+
+    @staticmethod
+    def _f(o):
+        return o.fn if isinstance(o, Lazy) else (lambda h, v=float(o): v)
+
+    def __add__(self, o):
+        a, b = self.fn, Lazy._f(o)
+        return Lazy(self.pool, lambda h: a(h) + b(h))
+    __radd__ = __add__
+
+    def __sub__(self, o):
+        a, b = self.fn, Lazy._f(o)
+        return Lazy(self.pool, lambda h: a(h) - b(h))
+
+    def __rsub__(self, o):
+        a, b = self.fn, Lazy._f(o)
+        return Lazy(self.pool, lambda h: b(h) - a(h))
+
+    def __mul__(self, o):
+        a, b = self.fn, Lazy._f(o)
+        return Lazy(self.pool, lambda h: a(h) * b(h))
+    __rmul__ = __mul__
+
+    def __truediv__(self, o):
+        a, b = self.fn, Lazy._f(o)
+        return Lazy(self.pool, lambda h: a(h) / b(h))
+
+    def __neg__(self):
+        a = self.fn
+        return Lazy(self.pool, lambda h: -a(h))
+
+
+class ScalarPool:
+    """Device vector collecting the scalar results of one evaluation (log-determinants, quadratic forms, the per-parameter
+    contractions of the gradient).  Every reduction writes its result to its slot on the device (``spde_*_dev``); the
+    host reads the vector once.  Replaces one device-to-host copy + stream synchronise per scalar."""
+
+    def __init__(self, cap: int = 2048):
+        self.buf = torch.zeros(cap, dtype=F64, device=_dev())
+        self.cap, self.used, self.host = cap, 0, None
+
+    def take(self, k: int = 1) -> int:
+        i = self.used
+        self.used += k
+        if self.used > self.cap:
+            raise _lib.SpdeError("ScalarPool: more than %d scalars in one evaluation" % self.cap)
+        return i
+
+    def addr(self, i: int) -> int:
+        return self.buf.data_ptr() + 8 * i
+
+    def scalar(self, i: int) -> Lazy:
+        return Lazy(self, lambda h: h[i])
+
+    def fetch(self) -> np.ndarray:
+        if self.host is None:
+            self.host = to_host(self.buf[:max(self.used, 1)])
+        return self.host
+
+    # reductions into the pool (same kernels as Engine.dot / wdot / residual_ss / logdet / gemv_t)
+    def dot(self, X, Y) -> Lazy:
+        i = self.take()
+        check(lib.spde_dot_dev(ptr(X), ptr(Y), X.numel(), self.addr(i), _stream()))
+        return self.scalar(i)
+
+    def wdot(self, X, Y, w) -> Lazy:
+        i = self.take()
+        check(lib.spde_wdot_dev(ptr(X), ptr(Y), ptr(w), X.shape[0], X.shape[1], self.addr(i), _stream()))
+        return self.scalar(i)
+
+    def residual_ss(self, data, mu, obs) -> Lazy:
+        i = self.take()
+        check(lib.spde_residual_ss_dev(ptr(data), ptr(mu), ptr(obs), data.shape[0], data.shape[1], self.addr(i), _stream()))
+        return self.scalar(i)
+
+    def logdet(self, engine, which: int) -> Lazy:
+        i = self.take()
+        check(lib.spde_logdet_dev(engine.plan.h, which, self.addr(i), _stream()))
+        return self.scalar(i)
+
+    def gemv_t(self, B, u) -> list:
+        """B^T u (B row-major rows x cols) as a list of cols pool scalars."""
+        cols = B.shape[1]
+        i = self.take(cols)
+        check(lib.spde_gemv_t(ptr(B), ptr(u), B.shape[0], cols, self.addr(i), _stream()))
+        return [self.scalar(i + c) for c in range(cols)]
+
+
 class Factor:
     """Drop-in for the ``sksparse.cholmod.Factor`` methods the reference uses
     (``advection_diffusion2D.py:194-202``, ``model.py:80,126``): ``logdet, solve_A, solve_Lt,

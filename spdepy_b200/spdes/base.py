@@ -21,7 +21,7 @@ import numpy as np
 import torch
 from scipy import sparse
 
-from ..engine import F64, Engine, to_dev, to_host
+from ..engine import F64, Engine, Lazy, ScalarPool, to_dev, to_host
 
 
 class SPDE2D:
@@ -445,6 +445,26 @@ class SPDE2D:
     def setClib(self) -> None:      # the reference compiles / loads its C++ here; nothing to do
         return None
 
+    # ------------------------------------------------------------------ scalar results: eager, or collected on the device
+    _pool = None         # ScalarPool of the evaluation in flight (logLike), None = every reduction returns a host float
+
+    def _dot(self, X, Y):
+        return Engine.dot(X, Y) if self._pool is None else self._pool.dot(X, Y)
+
+    def _wdot(self, X, Y, w):
+        return Engine.wdot(X, Y, w) if self._pool is None else self._pool.wdot(X, Y, w)
+
+    def _resid(self, data, mu, obs):
+        return Engine.residual_ss(data, mu, obs) if self._pool is None else self._pool.residual_ss(data, mu, obs)
+
+    def _logdet(self, eng, which):
+        return eng.logdet(which) if self._pool is None else self._pool.logdet(eng, which)
+
+    def _gemv_t(self, B, u, scale=1.0):
+        if self._pool is None:
+            return to_host(scale * Engine.gemv_t(B, u)).tolist()
+        return [scale * v for v in self._pool.gemv_t(B, u)]
+
     # ------------------------------------------------------------------ gradient contraction (K11)
     def _grad_from_weights(self, st, W, prior=None):
         """sum(W .* dQ_i) for every own parameter i (and the mod0 block when fitted jointly),
@@ -455,7 +475,7 @@ class SPDE2D:
         Ns = eng.Ns
         V, dt, sigma = st["V"], st["dt"], st["sigma"]
         GA, Gq, GQ0 = eng.assembly_adjoint(W, st["A9"], st["kappa"], V, sigma, dt, self.timed)
-        s_q0 = Engine.dot(GQ0, st["mod0"]["Q"]) if self.timed else 0.0
+        s_q0 = self._dot(GQ0, st["mod0"]["Q"]) if self.timed else 0.0
         s_prior_sigma = 0.0
         if prior is not None:
             # c*logdet Q = c*logdet Q0 + c*(T-1) (logdet B - Ns log(dt sigma)): weights c (T-1) Z_B on B, c Z_0 on Q0
@@ -476,9 +496,9 @@ class SPDE2D:
         else:
             u = V * kap * GAc
         if self.kvar:
-            out.extend(to_host(eng.gemv_t(self._bs_dev(), u.contiguous())).tolist())
+            out.extend(self._gemv_t(self._bs_dev(), u.contiguous()))
         else:
-            out.append(Engine.dot(u.contiguous(), torch.ones_like(u)))
+            out.append(self._dot(u.contiguous(), torch.ones_like(u)))
         # diffusion
         sgn = -dt if self.timed else -1.0
         wsd = to_dev(st["ws"]) if self.wkind is not None else None
@@ -489,7 +509,7 @@ class SPDE2D:
             f = st["faces"]
             D = torch.stack([GH[0], GH[1], GH[6], GH[7]], dim=1)        # dS/d(H00 at W,E), d(H11 at S,N)
             bsH = self._bsH_dev()
-            out.extend(to_host(sgn * eng.gemv_t(bsH, (f["gam"] * D).reshape(-1).contiguous())).tolist())
+            out.extend(self._gemv_t(bsH, (f["gam"] * D).reshape(-1).contiguous(), sgn))
             if self.Hkind == "ha":
                 # half-angle parametrisation H = gamma (cosh|v| I + sinh|v|/|v| [[vx,vy],[vy,-vx]])
                 out = out[:-self.Np]                                    # gamma block recomputed below (dH/dlog gamma = H)
@@ -504,38 +524,42 @@ class SPDE2D:
                 u_vx = gam * ((sh * vx / a + sg * (ds * vx / a * vx + s)) * D + ds * vx / a * vy * O)
                 u_vy = gam * ((sh * vy / a + sg * (ds * vy / a * vx)) * D + (ds * vy / a * vy + s) * O)
                 for u in (u_g, u_vx, u_vy):
-                    out.extend(to_host(sgn * eng.gemv_t(bsH, u.reshape(-1).contiguous())).tolist())
+                    out.extend(self._gemv_t(bsH, u.reshape(-1).contiguous(), sgn))
             elif self.Hkind == "aniso":
                 O = torch.stack([GH[2], GH[3], GH[4], GH[5]], dim=1)    # dS/d(H10 at W,E), d(H01 at S,N)
                 vx, vy = f["vx"], f["vy"]
                 u_vx = torch.cat([2 * vx[:, :2] * D[:, :2] + vy[:, :2] * O[:, :2], vy[:, 2:] * O[:, 2:]], dim=1)
                 u_vy = torch.cat([vx[:, :2] * O[:, :2], vx[:, 2:] * O[:, 2:] + 2 * vy[:, 2:] * D[:, 2:]], dim=1)
-                out.extend(to_host(sgn * eng.gemv_t(bsH, u_vx.reshape(-1).contiguous())).tolist())
-                out.extend(to_host(sgn * eng.gemv_t(bsH, u_vy.reshape(-1).contiguous())).tolist())
+                out.extend(self._gemv_t(bsH, u_vx.reshape(-1).contiguous(), sgn))
+                out.extend(self._gemv_t(bsH, u_vy.reshape(-1).contiguous(), sgn))
         else:
             GdG = None
             _, dirs = self._H_and_dirs(st["p"], want_dirs=True)
             for dH in dirs:
                 ah = eng.ah_stencil(g.hx, g.hy, to_dev(dH), self.Hvar)
-                out.append(sgn * Engine.dot(GA, ah))
+                out.append(sgn * self._dot(GA, ah))
         # advection
         if self.wkind == "const":
             for d in (1, 2):
-                out.append(dt * Engine.dot(GA, eng.aw_stencil(g.hx, g.hy, wsd, None, False, d, False)))
+                out.append(dt * self._dot(GA, eng.aw_stencil(g.hx, g.hy, wsd, None, False, d, False)))
         elif self.wkind == "cov":        # dA = Aw(ww) * dt   (cov_advection_diffusion2D.py:60,158-159)
-            out.append(dt * Engine.dot(GA, eng.aw_stencil(g.hx, g.hy, to_dev(self.ww), None, True, 3, False)))
+            out.append(dt * self._dot(GA, eng.aw_stencil(g.hx, g.hy, to_dev(self.ww), None, True, 3, False)))
         elif self.wkind == "var":
             if GdG is None:
                 _, GdG = eng.stencil_adjoint(g.hx, g.hy, GA, False, wsd)
             BAx, BAy = self._bsA_dev()
-            out.extend(to_host(dt * eng.gemv_t(BAx, GdG[:, [0, 2]].reshape(-1).contiguous())).tolist())
-            out.extend(to_host(dt * eng.gemv_t(BAy, GdG[:, [1, 3]].reshape(-1).contiguous())).tolist())
+            out.extend(self._gemv_t(BAx, GdG[:, [0, 2]].reshape(-1).contiguous(), dt))
+            out.extend(self._gemv_t(BAy, GdG[:, [1, 3]].reshape(-1).contiguous(), dt))
         if self.timed:
             # log sigma: dQ = -(Q - blockdiag(Q0-part))   (advection_diffusion2D.py:170-175)
-            s_total = Engine.dot(W, st["Q"])
+            s_total = self._dot(W, st["Q"])
             out.append(-(s_total - s_q0) + s_prior_sigma)
             if st["joint"]:
-                out.extend(self.mod0._grad_from_weights(st["mod0"], GQ0))
+                self.mod0._pool = self._pool
+                try:
+                    out.extend(self.mod0._grad_from_weights(st["mod0"], GQ0))
+                finally:
+                    self.mod0._pool = None
         return out
 
     def _bsH_dev(self):
@@ -580,7 +604,7 @@ class SPDE2D:
         e2.factorize_async(1, st["AtDA"])
         e0.factor_wait(0)
         e2.factor_wait(1)
-        ld0, ldB = e0.logdet(0), e2.logdet(1)
+        ld0, ldB = self._logdet(e0, 0), self._logdet(e2, 1)
         out = {"logdet": ld0 + (T - 1) * (ldB - Ns * np.log(st["dt"] * st["sigma"])), "logdetQ0": ld0, "logdetB": ldB}
         if want_grad:
             out["ZB"] = e2.selinv(1)
@@ -589,6 +613,31 @@ class SPDE2D:
 
     # ------------------------------------------------------------------ likelihood (advection_diffusion2D.py:187-223)
     def logLike(self, par, nh1=100, grad=True, probes=None, exact_grad=False):
+        """Every scalar of the evaluation (log-determinants, quadratic forms, traces, the per-parameter contractions)
+        is reduced into one device vector (:class:`ScalarPool`) and read back ONCE, when the likelihood and the gradient
+        are put together at the end -- the arithmetic below is written on lazy scalars exactly as the reference writes it
+        on NumPy floats (``advection_diffusion2D.py:198-223``)."""
+        self._pool = ScalarPool()
+        try:
+            return self._logLike(par, nh1, grad, probes, exact_grad)
+        finally:
+            self._pool = None
+
+    def _finish(self, like, norm, gi=None, g_last=None, npar=0):
+        """The one device-to-host read of the evaluation (lazy scalars -> floats) and the reference's return convention,
+        ``-like / (nobs r)`` and ``-grad / (nobs r)``."""
+        for k, v in list(self.last.items()):
+            if isinstance(v, Lazy):
+                self.last[k] = float(v)
+        like = float(like)
+        if gi is None:
+            return -like / norm
+        g_par = np.zeros(npar)
+        g_par[:len(gi)] = [float(v) for v in gi]
+        g_par[-1] = float(g_last)
+        return -like / norm, -g_par / norm
+
+    def _logLike(self, par, nh1, grad, probes, exact_grad):
         eng = self.engine
         par = np.asarray(par, dtype="float64")
         if self._obs is None or self.data is None:
@@ -622,28 +671,28 @@ class SPDE2D:
             eng.factorize_async(1, Q, cnt, tau)
             eng.factor_wait(0)
             eng.factor_wait(1)
-            ldQ = eng.logdet(0)
-        ldQc = eng.logdet(1)
+            ldQ = self._logdet(eng, 0)
+        ldQc = self._logdet(eng, 1)
         overlap = grad and exact_grad and collapsed
         if overlap:
             eng.selinv_start(1)     # the Takahashi pass runs beside the (latency-bound) solve and reductions below
         mu_c = eng.solve(1, eng.scatter_obs(data, obs, tau))          # Q_c^-1 S^T data tau
-        quad = Engine.dot(mu_c, eng.q_apply(Q, mu_c))
-        resid = Engine.residual_ss(data, mu_c, obs)
+        quad = self._dot(mu_c, eng.q_apply(Q, mu_c))
+        resid = self._resid(data, mu_c, obs)
         like = 1 / 2 * ldQ * r + nobs * r * np.log(tau) / 2 - 1 / 2 * ldQc * r - 1 / 2 * quad - tau / 2 * resid
         self.last = {"mu_c": mu_c, "logdetQ": ldQ, "logdetQc": ldQc, "quad": quad, "resid": resid}
         if not grad:
-            return -like / (nobs * r)
+            return self._finish(like, nobs * r)
         if exact_grad and collapsed:
             W = eng.selinv_fetch(1)
             nd = eng.nslots // 2
-            tr_tau = Engine.dot(cnt, W[nd * eng.n:(nd + 1) * eng.n]) * tau
+            tr_tau = self._dot(cnt, W[nd * eng.n:(nd + 1) * eng.n]) * tau
             W *= -0.5 * r
             prior["c"] = 0.5 * r
         elif exact_grad:
             Z, Zc = eng.selinv_pair()
             nd = eng.nslots // 2
-            tr_tau = Engine.dot(cnt, Zc[nd * eng.n:(nd + 1) * eng.n].contiguous()) * tau
+            tr_tau = self._dot(cnt, Zc[nd * eng.n:(nd + 1) * eng.n].contiguous()) * tau
             W = (Z - Zc) * (0.5 * r)
             del Z, Zc
         else:
@@ -656,13 +705,11 @@ class SPDE2D:
             a = 0.5 * r / nh1
             W = eng.sddmm(TrQ, Vp, a)
             W = eng.sddmm(TrQc, Vp, -a, W)
-            tr_tau = Engine.wdot(TrQc, Vp, cnt) * tau / nh1
+            tr_tau = self._wdot(TrQc, Vp, cnt) * tau / nh1
         W = eng.sddmm(mu_c, mu_c, -0.5, W)
-        g_par = np.zeros(par.size)
         gi = self._grad_from_weights(st, W, prior)
-        g_par[:len(gi)] = gi
-        g_par[-1] = nobs * r / 2 - 1 / 2 * tr_tau * r - tau / 2 * resid
-        return -like / (nobs * r), -g_par / (nobs * r)
+        g_last = nobs * r / 2 - 1 / 2 * tr_tau * r - tau / 2 * resid
+        return self._finish(like, nobs * r, gi, g_last, par.size)
 
 
     def _logLike_streamed(self, par, st, data, obs, cnt, tau, grad):
@@ -679,30 +726,28 @@ class SPDE2D:
         b = eng.scatter_obs(data, obs, tau)
         if not grad:
             ldQc, y, _ = eng.streamed_eval(Q, cnt, tau, X=b, mode=1 | 4, selinv=False)
-            yy = Engine.dot(data, data)
-            half = 0.5 * (tau * yy - Engine.dot(y, y))
+            yy = self._dot(data, data)
+            half = 0.5 * (tau * yy - self._dot(y, y))
             like = 1 / 2 * ldQ * r + nobs * r * np.log(tau) / 2 - 1 / 2 * ldQc * r - half
             self.last = {"mu_c": None, "logdetQ": ldQ, "logdetQc": ldQc}
-            return -like / (nobs * r)
+            return self._finish(like, nobs * r)
         ldQc, mu_c, W = eng.streamed_eval(Q, cnt, tau, X=b, mode=15, selinv=True)
-        quad = Engine.dot(mu_c, eng.q_apply(Q, mu_c))
-        resid = Engine.residual_ss(data, mu_c, obs)
+        quad = self._dot(mu_c, eng.q_apply(Q, mu_c))
+        resid = self._resid(data, mu_c, obs)
         like = 1 / 2 * ldQ * r + nobs * r * np.log(tau) / 2 - 1 / 2 * ldQc * r - 1 / 2 * quad - tau / 2 * resid
         self.last = {"mu_c": mu_c, "logdetQ": ldQ, "logdetQc": ldQc, "quad": quad, "resid": resid}
         nd = eng.nslots // 2
-        tr_tau = Engine.dot(cnt, W[nd * eng.n:(nd + 1) * eng.n]) * tau
+        tr_tau = self._dot(cnt, W[nd * eng.n:(nd + 1) * eng.n]) * tau
         if getattr(self, "check_selinv", False):
             # size-independent checksum of the selected inverse: the pattern of Q_c is inside the extracted pattern,
             # so sum_e (Q_c)_e Z_e = tr(Q_c Q_c^-1) = n exactly
-            self.last["selinv_trace_over_n"] = (Engine.dot(Q, W) + tr_tau) / eng.n
+            self.last["selinv_trace_over_n"] = (self._dot(Q, W) + tr_tau) / eng.n
         W *= -0.5 * r
         prior["c"] = 0.5 * r
         W = eng.sddmm(mu_c, mu_c, -0.5, W)
-        g_par = np.zeros(par.size)
         gi = self._grad_from_weights(st, W, prior)
-        g_par[:len(gi)] = gi
-        g_par[-1] = nobs * r / 2 - 1 / 2 * tr_tau * r - tau / 2 * resid
-        return -like / (nobs * r), -g_par / (nobs * r)
+        g_last = nobs * r / 2 - 1 / 2 * tr_tau * r - tau / 2 * resid
+        return self._finish(like, nobs * r, gi, g_last, par.size)
 
 
 class LazyDQ:

@@ -5,7 +5,7 @@
 HBM-bound kernels (assembly K2/K3, scatter K4, logdet K6, k=1 solves K7, reductions K8/K9, adjoint K11 and
 the helper kernels of the factor / Takahashi schedules) are timed with CUDA events on the stream they are
 launched on, L2 flushed between repetitions, and reported as ALGORITHMIC bytes / time against the measured
-HBM copy bandwidth (MEASURED_PEAKS.json, 6449 GB/s on this pool).  The assembly kernels are additionally
+HBM copy bandwidth (MEASURED_PEAKS.json, 6546.9 GB/s on this pool).  The assembly kernels are additionally
 timed on the 256x256x100 mesh (BASELINE configs[3]): the precision itself (2.25 GB) fits, only its factor
 does not.  The dense kernels are reported in TFLOP/s against cuBLAS DGEMM measured in the same run.
 """
@@ -28,7 +28,7 @@ try:
     HBM = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
     HBM_SRC = "MEASURED_PEAKS.json"
 except Exception:
-    HBM, HBM_SRC = 6449.1, "fallback (MEASURED_PEAKS.json of this pool, 2026-10-17)"
+    HBM, HBM_SRC = 6546.9, "fallback (MEASURED_PEAKS.json of this pool, 2026-10-17)"
 
 _flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 rows = []
@@ -137,6 +137,21 @@ def main():
     P1, P2 = pe.Program(plan, 1, 1), pe.Program(plan, 2, 1)
     hbm_row(tag, "solve_A k=1 (k_gemv_grouped x%d, graph)" % (len(P1.launches) + len(P2.launches)), "Factor.solve_A(b), one column",
             16 * stats["nnzL"] + 32 * n, t, len(P1.launches) + len(P2.launches))
+
+    # ---- the reference's default (Hutchinson) gradient: 100 probe columns (advection_diffusion2D.py:200-207)
+    nh1 = 100
+    Vp = (2.0 * torch.randint(0, 2, (n, nh1), device="cuda") - 1.0).to(F64)
+    Xs = Vp.clone()
+    eng.solve(1, Xs)
+    t = timeit(lambda: eng.solve(1, Xs.copy_(Vp)), reps=3)
+    rows.append({"mesh": tag, "kernel": "solve_A k=100 (grouped FP64 GEMM tiles, graph)", "bound": "tensor", "ms": t,
+                 "tflops": 4.0 * stats["nnzL"] * nh1 / (t * 1e-3) / 1e12, "flops": 4.0 * stats["nnzL"] * nh1})
+    Wh = torch.zeros(43 * n, dtype=F64, device="cuda")
+    t = timeit(lambda: eng.sddmm(Xs, Vp, 0.005, Wh))
+    hbm_row(tag, "k_sddmm (k=100, accumulate)", "V .* (dQ_i@Q^-1 V) for all i (npar SpMMs)", 8 * (2 * n * nh1 + 2 * 43 * n), t)
+    t = timeit(lambda: Engine.wdot(Xs, Vp, cnt))
+    hbm_row(tag, "k_wdot_partial+k_final (k=100)", "tau trace sum(V .* S^T S Q_c^-1 V)", 8 * (2 * n * nh1 + n), t, 2)
+    del Vp, Xs, Wh
 
     # ---- helper kernels of the schedules, from the per-launch profile
     kinds = ["gemm", "potrf", "extend_add", "memset", "gather", "wtw", "extract", "gemv"]
