@@ -512,7 +512,7 @@ def run_streamed(args):
         "e2e": {"value": blk["evals_per_s"], "unit": UNIT, "h2d_bytes_per_step": blk["h2d_bytes_per_eval"],
                 "d2h_bytes_per_step": blk["d2h_bytes_per_eval"]},
         "gpu_launches": blk["gpu_launches"], "clocks": blk["clocks"],
-        "roofline": {"bound": "tensor", "kernel": "k_gemm_grouped (FP64 DMMA m8n8k4)", "achieved": blk["roofline_achieved_tflops"],
+        "roofline": {"bound": "tensor", "kernel": "k_gemm_ws + k_gemm_grouped (FP64 DMMA m8n8k4; bulk-async warp-specialised tiles / cp.async ring tiles)", "achieved": blk["roofline_achieved_tflops"],
                      "peak": blk["roofline_peak_tflops"], "unit": "TFLOP/s", "frac": blk["roofline_frac"], "traffic": None,
                      "peak_source": "cuBLAS DGEMM 8192^3 measured in this run", "note": blk["note"]},
         "cpu_baseline": None if args.no_cpu else cpu_baseline(name),
@@ -669,13 +669,13 @@ def incore_region(args, rank, world, local):
         if os.path.exists(tpath) and not hutch:
             tj = json.load(open(tpath))
             traffic = tj["traffic_bytes_per_launch"]
-            traffic_note = ("dram__bytes_read.sum + dram__bytes_write.sum summed over the %d k_gemm_grouped launches of one "
+            traffic_note = ("dram__bytes_read.sum + dram__bytes_write.sum summed over the %d dense-tile launches (k_gemm_ws, k_gemm_grouped) of one "
                             "evaluation (%.0f GB read, %.0f GB written) / launches, from %s"
                             % (tj["launches"], tj["dram_read_bytes"] / 1e9, tj["dram_write_bytes"] / 1e9, os.path.basename(tpath)))
             break
     by_kind = {k: float(pms[i].sum()) for i, k in enumerate(
         ["gemm", "potrf", "extend_add", "memset", "gather", "wtw", "extract", "gemv"])}
-    roof = {"bound": "tensor", "kernel": "k_gemm_grouped (FP64 DMMA m8n8k4)", "achieved": achieved, "peak": peak,
+    roof = {"bound": "tensor", "kernel": "k_gemm_ws + k_gemm_grouped (FP64 DMMA m8n8k4; bulk-async warp-specialised tiles / cp.async ring tiles)", "achieved": achieved, "peak": peak,
             "unit": "TFLOP/s", "frac": (achieved / peak) if achieved else None, "traffic": traffic,
             "traffic_note": traffic_note,
             "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (MEASURED_PEAKS.json has no FP64 figure)",

@@ -172,11 +172,18 @@ struct LevelBuilder {
                 prog.gemm.push_back(t);
                 const int tm = (t.M + BM - 1) / BM, tn = (t.N + BN - 1) / BN;
                 const bool lower = t.flags & GF_LOWER;
-                for (int tj = 0; tj < tn; tj++)
-                    for (int ti = 0; ti < tm; ti++) {
-                        if (lower && (ti + 1) * BM - 1 < tj * BN) continue;
-                        prog.tiles.push_back(TileRef{id, ti, tj, 0});
-                    }
+                // L2-aware raster: CTAs are dispatched in tile order and the ~300 resident ones walk K in step, so an
+                // operand panel is fetched from DRAM once per group of resident tiles that share it.  Column-major order
+                // makes ~4 tile columns resident: every A row panel is shared by 4 tiles only.  Supertiles of SJ x SI
+                // (16 x 16, or all columns x 256/columns for narrow products) share A panels 16-fold and B panels 16-fold.
+                const int SJ = std::min(tn, 16), SI = std::max(1, 256 / SJ);
+                for (int tj0 = 0; tj0 < tn; tj0 += SJ)
+                    for (int ti0 = 0; ti0 < tm; ti0 += SI)
+                        for (int tj = tj0; tj < std::min(tj0 + SJ, tn); tj++)
+                            for (int ti = ti0; ti < std::min(ti0 + SI, tm); ti++) {
+                                if (lower && (ti + 1) * BM - 1 < tj * BN) continue;
+                                prog.tiles.push_back(TileRef{id, ti, tj, 0});
+                            }
                 // lower: the trapezoid on and below the diagonal of an M x N block (M >= N)
                 prog.flops += 2.0 * t.K * (lower ? (double)t.M * t.N - 0.5 * t.N * std::min(t.M, t.N) : (double)t.M * t.N);
             }

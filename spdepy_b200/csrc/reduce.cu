@@ -112,7 +112,10 @@ __global__ void k_final(const double *__restrict__ partial, int m, double *__res
     if (threadIdx.x == 0) out[0] = s;
 }
 
-// one warp per node: lanes stride over the k probe columns, one shuffle reduction per slot
+// one warp per node: lanes stride over the k probe columns, one shuffle reduction per slot.  For k <= 128 (the reference's
+// nh1 = 100) the node's own row stays in registers and four slots are reduced together, so that four independent
+// load -> FMA -> shuffle chains are in flight per warp instead of one (the kernel is latency-bound: every dot product is a
+// chain of L2 loads, dependent FP64 adds and five shuffle rounds).
 __global__ void k_sddmm(Geo g, const double *__restrict__ X, const double *__restrict__ Y, int k, double alpha,
                         int accumulate, double *__restrict__ W)
 {
@@ -121,6 +124,41 @@ __global__ void k_sddmm(Geo g, const double *__restrict__ X, const double *__res
     const int lane = threadIdx.x & 31;
     const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    if (k <= 128) {
+        for (long long node = warp0; node < n; node += nwarps) {
+            double xr[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) { const int p = lane + 32 * u; xr[u] = p < k ? X[node * k + p] : 0.0; }
+            for (int q0 = 0; q0 < ns; q0 += 4) {
+                int c[4];
+                double s[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) c[j] = (q0 + j < ns) ? g.slot_nbr((int)node, q0 + j) : -1;
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    s[j] = 0.0;
+                    if (c[j] >= 0) {
+                        const double *y = Y + (long long)c[j] * k;
+#pragma unroll
+                        for (int u = 0; u < 4; u++) { const int p = lane + 32 * u; if (p < k) s[j] += xr[u] * y[p]; }
+                    }
+                }
+#pragma unroll
+                for (int o = 16; o; o >>= 1)
+#pragma unroll
+                    for (int j = 0; j < 4; j++) s[j] += __shfl_down_sync(0xffffffffu, s[j], o);
+                if (lane == 0) {
+#pragma unroll
+                    for (int j = 0; j < 4; j++)
+                        if (c[j] >= 0) {
+                            const long long o = (long long)(q0 + j) * n + node;
+                            W[o] = accumulate ? W[o] + alpha * s[j] : alpha * s[j];
+                        }
+                }
+            }
+        }
+        return;
+    }
     for (long long node = warp0; node < n; node += nwarps) {
         for (int q = 0; q < ns; q++) {
             const int c = g.slot_nbr((int)node, q);

@@ -21,7 +21,7 @@ import numpy as np
 import torch
 from scipy import sparse
 
-from ..engine import F64, Engine, Lazy, ScalarPool, to_dev, to_host
+from ..engine import COUNTERS, F64, Engine, Lazy, ScalarPool, to_dev, to_host
 
 
 class SPDE2D:
@@ -669,6 +669,12 @@ class SPDE2D:
             prior = None
             eng.factorize_async(0, Q)               # the two factorisations run concurrently
             eng.factorize_async(1, Q, cnt, tau)
+            if grad and not exact_grad and probes is None:
+                # the reference's draw (advection_diffusion2D.py:200), from the same global legacy stream, made while the
+                # device factorises; the +-1 matrix crosses PCIe as one byte per entry and is widened on the device
+                r8 = np.random.randint(1, 3, self.grid.n * nh1).astype(np.int8)
+                COUNTERS["h2d"] += r8.nbytes
+                probes = (2.0 * torch.from_numpy(r8).to(device=Q.device, non_blocking=False).to(F64) - 3.0).reshape(self.grid.n, nh1)
             eng.factor_wait(0)
             eng.factor_wait(1)
             ldQ = self._logdet(eng, 0)
@@ -698,7 +704,7 @@ class SPDE2D:
         else:
             if probes is None:
                 probes = (2 * np.random.randint(1, 3, self.grid.n * nh1) - 3).reshape(self.grid.n, nh1)
-            Vp = to_dev(np.asarray(probes, dtype=np.float64))
+            Vp = probes if isinstance(probes, torch.Tensor) else to_dev(np.asarray(probes, dtype=np.float64))
             nh1 = Vp.shape[1]
             TrQ = eng.solve(0, Vp.clone())
             TrQc = eng.solve(1, Vp.clone())

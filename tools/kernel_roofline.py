@@ -185,7 +185,7 @@ def main():
                 g = P.gemm[L["task0"]:L["task0"] + L["ntasks"]]
                 a["flops"] += float((2.0 * g["M"] * g["N"] * g["K"]).sum())
         for k, a in sorted(agg.items()):
-            if k == pe.LK_GEMM:
+            if k == pe.LK_GEMM or k >= 8:        # (lane fork / join records are not launches)
                 continue
             kn = {1: "k_potrf (64x64 + inverse)", 2: "k_extend_add", 3: "cudaMemsetAsync (L store / arenas)", 4: "k_selinv_gather",
                   5: "k_wtw", 6: "k_extract", 7: "k_gemv_grouped"}[k]

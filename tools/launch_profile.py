@@ -62,7 +62,7 @@ for prog, pname in ((0, "factor"), (3, "selinv")):
             print("   tiles in [%5d,%6s) launches %5d  ms %9.2f  flop %.3g  -> %.2f TFLOP/s   (mean K %.0f, mean tasks %.1f)" % (
                 lo, "inf" if hi > 1 << 29 else str(hi), msk.sum(), rows[msk, 0].sum(), rows[msk, 1].sum(),
                 rows[msk, 1].sum() / max(rows[msk, 0].sum(), 1e-9) / 1e9, rows[msk, 7].mean(), rows[msk, 3].mean()))
-    other = [(kinds[L["kind"]], ms[i]) for i, L in enumerate(P.launches) if L["kind"] != 0]
+    other = [(kinds[L["kind"]], ms[i]) for i, L in enumerate(P.launches) if 0 < L["kind"] < len(kinds)]      # (not the sync records)
     agg = {}
     for k, v in other:
         agg[k] = agg.get(k, 0.0) + float(v)
