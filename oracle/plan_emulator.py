@@ -14,7 +14,7 @@ import numpy as np
 
 GF_LOWER, GF_BETA0, GF_NEG, GF_ATOMIC, GF_GATHER_A, GF_SCATTER_C, GF_MIRROR = (1 << 9, 1 << 10, 1 << 11, 1 << 12,
                                                                             1 << 13, 1 << 14, 1 << 15)
-LK_GEMM, LK_POTRF, LK_EXTADD, LK_ZERO, LK_GATHER, LK_WTW, LK_EXTRACT, LK_GEMV, LK_SYNC, LK_COPY = range(10)
+LK_GEMM, LK_POTRF, LK_EXTADD, LK_ZERO, LK_GATHER, LK_WTW, LK_EXTRACT, LK_GEMV, LK_SYNC, LK_COPY, LK_BCOPY = range(11)
 NB = 64
 CFG = {0: (128, 128), 1: (128, 64), 2: (64, 64), 3: (128, 64)}      # 3 = warp-specialised bulk-async kernel
 
@@ -31,6 +31,8 @@ EXT = np.dtype([("src", "i8"), ("lds", "i4"), ("nr", "i4"), ("ppanel", "i8"), ("
 GATHER = np.dtype([("dst", "i8"), ("ldd", "i4"), ("ncp", "i4"), ("nr", "i4"), ("src", "i8"), ("lds", "i4"),
                    ("pnc", "i4"), ("pncp", "i4"), ("rel", "i4"), ("src_space", "i4"), ("dst_space", "i4")], align=True)
 WTW = np.dtype([("w", "i8"), ("dst", "i8"), ("ldd", "i4"), ("b", "i4"), ("space", "i4"), ("pad", "i4")], align=True)
+BCOPY = np.dtype([("dst", "i8"), ("src", "i8"), ("ldd", "i4"), ("lds", "i4"), ("rows", "i4"), ("cols", "i4"),
+                  ("dst_space", "i4"), ("src_space", "i4")], align=True)
 ZENT = np.dtype([("dst", "i8"), ("dst2", "i8"), ("src", "i8"), ("sn", "i4"), ("pad", "i4")], align=True)
 
 
@@ -51,6 +53,10 @@ class Program:
         self.ext = ex(prog, 4, EXT, k)
         self.gather = ex(prog, 5, GATHER, k)
         self.wtw = ex(prog, 6, WTW, k)
+        try:
+            self.bcopy = ex(prog, 8, BCOPY, k)
+        except Exception:       # (the streamed evaluator's export has no block-copy table)
+            self.bcopy = np.zeros(0, BCOPY)
 
 
 class Emulator:
@@ -70,6 +76,7 @@ class Emulator:
         self.sp[1] = np.zeros(max(a0, 1))
         self.sp[2] = np.zeros(max(a1, 1))
         self.sp[3] = np.zeros(max(self.dinv_size, 2))
+        self.sp[5] = np.zeros(max(self.ybuf_size, 2))      # scratch of the outer-block products (factor and Takahashi)
         self.zsizes = (z0, z1)
         self.status = 0
 
@@ -226,6 +233,10 @@ class Emulator:
                 self._gather(P, L)
             elif kind == LK_WTW:
                 self._wtw(P, L)
+            elif kind == LK_BCOPY:
+                for t in P.bcopy[L["task0"]:L["task0"] + L["ntasks"]]:
+                    src = np.array(self._view(int(t["src_space"]), int(t["src"]), int(t["lds"]), int(t["rows"]), int(t["cols"])))
+                    self._view(int(t["dst_space"]), int(t["dst"]), int(t["ldd"]), int(t["rows"]), int(t["cols"]))[:, :] = src
             elif kind == LK_SYNC:
                 continue        # lane ordering: the launch list is a valid serial order
             elif kind == LK_COPY:
@@ -282,7 +293,6 @@ class Emulator:
 
     def selinv(self):
         """``spde_selinv``: returns Z on the pattern of Q, flat slot-major (nslots*n)."""
-        self.sp[5] = np.zeros(max(self.ybuf_size, 2))
         self.sp[6] = np.zeros(max(self.zsizes[0], 1))
         self.sp[7] = np.zeros(max(self.zsizes[1], 1))
         zent = self.plan.export(4, 5, ZENT)

@@ -333,6 +333,20 @@ __global__ void __launch_bounds__(256) k_wtw(const WtwTask *__restrict__ tasks, 
             if (jg + u < t.b) dst[i + (long long)(jg + u) * t.ldd] = acc[u];
     }
 }
+// rectangular block copy (LK_BCOPY): one CTA per 512 x 8 patch, coalesced along the rows
+__global__ void __launch_bounds__(256) k_block_copy(const CopyTask *__restrict__ tasks, const TileRef *__restrict__ tiles, GemmSpaces sp)
+{
+    pdl_enter();
+    const TileRef tr = tiles[blockIdx.x];
+    const CopyTask t = tasks[tr.task];
+    const double *src = sp.base[t.src_space] + t.src;
+    double *dst = sp.base[t.dst_space] + t.dst;
+    const int r0 = tr.ti * 512, c0 = tr.tj * 8;
+    for (int e = threadIdx.x; e < 512 * 8; e += 256) {
+        const int r = r0 + (e & 511), c = c0 + (e >> 9);
+        if (r < t.rows && c < t.cols) dst[r + (long long)c * t.ldd] = src[r + (long long)c * t.lds];
+    }
+}
 __global__ void k_extract(const ZEntry *__restrict__ ent, long long a0, long long a1, const double *__restrict__ zar,
                           double *__restrict__ Zq)
 {
@@ -443,6 +457,7 @@ static int upload_program(Program &P)
     SPDE_CUDA_CHECK(upload(P.ext, &P.d_ext));
     SPDE_CUDA_CHECK(upload(P.gather, &P.d_gather));
     SPDE_CUDA_CHECK(upload(P.wtw, &P.d_wtw));
+    SPDE_CUDA_CHECK(upload(P.bcopy, &P.d_bcopy));
     P.uploaded = true;
     return SPDE_OK;
 }
@@ -450,7 +465,7 @@ static int upload_program(Program &P)
 static void free_program(Program &P)
 {
     for (int w = 0; w < 2; w++) if (P.graph[w]) { cudaGraphExecDestroy(P.graph[w]); P.graph[w] = nullptr; }
-    cudaFree(P.d_gemm); cudaFree(P.d_tiles); cudaFree(P.d_potrf); cudaFree(P.d_ext); cudaFree(P.d_gather); cudaFree(P.d_wtw);
+    cudaFree(P.d_gemm); cudaFree(P.d_tiles); cudaFree(P.d_potrf); cudaFree(P.d_ext); cudaFree(P.d_gather); cudaFree(P.d_wtw); cudaFree(P.d_bcopy);
     P.uploaded = false;
 }
 
@@ -570,6 +585,9 @@ int issue_program_ex(Plan &p, Program &P, const ExecCtx &ctx, cudaStream_t st)
         case LK_WTW:
             SPDE_CUDA_CHECK(launch_pdl(k_wtw, dim3(L.ntasks), dim3(256), 0, st, P.d_wtw + L.task0, (const double *)ctx.dinv, sp));
             break;
+        case LK_BCOPY:
+            SPDE_CUDA_CHECK(launch_pdl(k_block_copy, dim3(L.ntiles), dim3(256), 0, st, P.d_bcopy + L.task0, P.d_tiles + L.tile0, sp));
+            break;
         case LK_EXTRACT: {
             const long long cnt = L.a1 - L.a0;
             SPDE_CUDA_CHECK(launch_pdl(k_extract, dim3((int)std::min<long long>((cnt + 255) / 256, 148 * 16)), dim3(256), 0, st,
@@ -592,8 +610,9 @@ int issue_program_ex(Plan &p, Program &P, const ExecCtx &ctx, cudaStream_t st)
             const Launch &L = P.launches[i];
             if (L.kind == LK_SYNC || L.kind == LK_COPY) continue;
             const int v = L.kind == LK_GEMM ? L.variant : 0;
-            p.prof_ms[L.kind][v] += ms;
-            p.prof_cnt[L.kind][v] += 1;
+            const int kd = L.kind == LK_BCOPY ? (int)LK_GATHER : L.kind;      // block copies are accounted with the gathers
+            p.prof_ms[kd][v] += ms;
+            p.prof_cnt[kd][v] += 1;
         }
         for (auto &e : ev) cudaEventDestroy(e);
     }
@@ -751,6 +770,8 @@ static int ensure_device(Plan &p, int which)
         SPDE_CUDA_CHECK(cudaMalloc((void **)&p.d_dinv[which], std::max<int64_t>(p.dinv_size, 2) * sizeof(double)));
         // (the outer-block inverses behind the 64x64 blocks are lower triangular: their upper blocks are never written)
         SPDE_CUDA_CHECK(cudaMemset(p.d_dinv[which], 0, std::max<int64_t>(p.dinv_size, 2) * sizeof(double)));
+        // scratch of the outer-block products (factorisation: doubling rounds and the out-of-place TRSM; Takahashi: Yt)
+        SPDE_CUDA_CHECK(cudaMalloc((void **)&p.d_ybuf[which], std::max<int64_t>(p.ybuf_size, 2) * sizeof(double)));
     }
     return SPDE_OK;
 }
@@ -874,6 +895,7 @@ extern "C" int spde_plan_export(spde_plan *pp, int prog, int k, int what, void *
         case 5: EXP(P->gather) break;
         case 6: EXP(P->wtw) break;
         case 7: EXP(P->last_ms) break;
+        case 8: EXP(P->bcopy) break;
         default: set_error("spde_plan_export: bad what"); return SPDE_ERR_ARG;
         }
     } else if (prog == 4) {   // layout
@@ -1029,7 +1051,6 @@ extern "C" int spde_selinv_start(spde_plan *pp, int which, void *stream)
     if (!p.sel_ready[which]) {
         for (int a = 0; a < 2; a++)
             if (p.zarena_size[a]) SPDE_CUDA_CHECK(cudaMalloc((void **)&p.d_zarena[which][a], p.zarena_size[a] * sizeof(double)));
-        SPDE_CUDA_CHECK(cudaMalloc((void **)&p.d_ybuf[which], std::max<int64_t>(p.ybuf_size, 2) * sizeof(double)));
         SPDE_CUDA_CHECK(cudaMalloc((void **)&p.d_zq[which], zbytes));
         if (!p.d_zentries) SPDE_CUDA_CHECK(upload(p.zentries, &p.d_zentries));
         p.sel_ready[which] = 1;

@@ -41,8 +41,11 @@ struct GatherTask {   // selected inverse: child's trailing block <- parent's fr
     int src_space, dst_space;
 };
 struct WtwTask { long long w; long long dst; int ldd, b, space, pad; };
+// rectangular block copy dst(rows x cols, ldd) <- src(rows x cols, lds): the outer-block TRSM of the factorisation is
+// computed out of place (scratch in the Y space) and copied back into the panel
+struct CopyTask { long long dst, src; int ldd, lds, rows, cols, dst_space, src_space; };
 
-enum LaunchKind : int { LK_GEMM = 0, LK_POTRF, LK_EXTADD, LK_ZERO, LK_GATHER, LK_WTW, LK_EXTRACT, LK_GEMV, LK_SYNC, LK_COPY };
+enum LaunchKind : int { LK_GEMM = 0, LK_POTRF, LK_EXTADD, LK_ZERO, LK_GATHER, LK_WTW, LK_EXTRACT, LK_GEMV, LK_SYNC, LK_COPY, LK_BCOPY };
 // LK_SYNC (two-lane schedules): variant 0 = the bulk lane waits for everything issued so far on the main lane,
 // 1 = record bulk-lane event a0, 2 = the main lane waits for bulk-lane event a0.  The launch list is always a valid
 // serial order, so an executor may ignore the lanes (profiling mode, the NumPy interpreter).
@@ -65,9 +68,10 @@ struct Program {
     std::vector<ExtTask> ext;
     std::vector<GatherTask> gather;
     std::vector<WtwTask> wtw;
+    std::vector<CopyTask> bcopy;
     // device copies
     GemmTask *d_gemm = nullptr; TileRef *d_tiles = nullptr; PotrfTask *d_potrf = nullptr;
-    ExtTask *d_ext = nullptr; GatherTask *d_gather = nullptr; WtwTask *d_wtw = nullptr;
+    ExtTask *d_ext = nullptr; GatherTask *d_gather = nullptr; WtwTask *d_wtw = nullptr; CopyTask *d_bcopy = nullptr;
     bool uploaded = false;
     double flops = 0;
     // CUDA graph of the whole schedule, per factor store; re-captured when a base pointer changes
@@ -95,6 +99,7 @@ struct Plan {
     std::map<std::pair<int, int>, Program> solve;   // (k, direction) -> program
     Program selinv;
     bool selinv_built = false;
+    bool winv_from_factor = false;   // the factorisation leaves the outer-block inverses Wf behind (diagonal-first panels)
     // device state
     int device_ready = 0;
     double *d_L[2] = {nullptr, nullptr};

@@ -138,6 +138,11 @@ void Plan::build_factor_program()
     const bool lookahead = envl ? atoi(envl) != 0 : false;
     const char *envo = getenv("SPDE_FACTOR_OUTER");     // test hook: small outer blocks exercise the look-ahead on small meshes
     const int OUTER = envo ? std::max(1, atoi(envo)) : spde::OUTER;
+    // Diagonal-first panels with outer-block inverses (factor_node_steps_diag) on the fronts that have a winv store.
+    // Measured on B200 (profiles/r2_factor_diag_ab.txt): C3 factorisation 261 ms with vs 253 ms without, C2 11.8 vs 10.2 ms
+    // -- every launch of the dependent chain costs ~10 us whatever its height, and the variant adds nine launches per outer
+    // block (copy, six doubling products, the strip product, the copy back) to save tile rows, not launches.  Off by default.
+    winv_from_factor = !lookahead && !envo && env_int("SPDE_FACTOR_DIAG", 0, 0) != 0;
     // The update-matrix arena of level d-1 is the arena the extend-add of level d has just consumed, so it is zeroed on the
     // side lane under the (compute-bound) factorisation of level d instead of in front of level d-1: LK_SYNC records fork
     // and join the lane; executors without lanes run the list in order, which is just as valid.
@@ -295,9 +300,12 @@ void Plan::build_factor_program()
             continue;
         }
         LevelBuilder B(P);
+        int64_t yoff = 0;
         for (int s : lev) {
             std::vector<Step> q;
-            factor_node_steps(B, sn[s], sp_u, OUTER, q);
+            if (winv_from_factor && sn[s].winv >= 0) factor_node_steps_diag(B, sn[s], sp_u, yoff, q);
+            else factor_node_steps(B, sn[s], sp_u, OUTER, q);
+            yoff += sn[s].winv >= 0 ? ybuf_need(sn[s]) : (int64_t)sn[s].ld * NB;
             B.seq.push_back(std::move(q));
         }
         B.flush();
@@ -416,7 +424,7 @@ void Plan::build_selinv_program()
                 else { single.push_back(&sn[s]); yoff += (int64_t)sn[s].ld * NB; }
             }
             wtw_level_launch(P, single, sp_z);
-            if (!multi.empty()) winv_level_launches(P, multi, ymulti, sp_z);
+            if (!multi.empty()) winv_level_launches(P, multi, ymulti, sp_z, winv_from_factor);
         }
         LevelBuilder B(P);
         for (size_t i = 0; i < lev.size(); i++) {

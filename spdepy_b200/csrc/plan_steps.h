@@ -43,6 +43,7 @@ struct Step {
     int g0, gn;          // range in the level's GEMM pool
     PotrfTask p;
     WtwTask w;
+    CopyTask cp;
     Launch raw;          // LK_COPY: the launch record itself
 };
 
@@ -232,6 +233,22 @@ struct LevelBuilder {
                 prog.launches.push_back(L);
             } else if (best.first == LK_COPY) {
                 for (const Step *st : chosen) prog.launches.push_back(st->raw);
+            } else if (best.first == LK_BCOPY) {
+                Launch L;
+                memset(&L, 0, sizeof L);
+                L.kind = LK_BCOPY;
+                L.task0 = (int64_t)prog.bcopy.size();
+                L.tile0 = (int64_t)prog.tiles.size();
+                for (const Step *st : chosen) {
+                    const int id = (int)(prog.bcopy.size() - L.task0);
+                    prog.bcopy.push_back(st->cp);
+                    const int tr = (st->cp.rows + 511) / 512, tc = (st->cp.cols + 7) / 8;     // 512 x 8 patches
+                    for (int tj = 0; tj < tc; tj++)
+                        for (int ti = 0; ti < tr; ti++) prog.tiles.push_back(TileRef{id, ti, tj, 0});
+                }
+                L.ntasks = (int)(prog.bcopy.size() - L.task0);
+                L.ntiles = (int)(prog.tiles.size() - L.tile0);
+                if (L.ntiles > 0) prog.launches.push_back(L);
             } else if (best.first == LK_WTW) {
                 Launch L;
                 memset(&L, 0, sizeof L);
@@ -357,6 +374,15 @@ static inline void factor_node_steps(LevelBuilder &B, const SNode &x, int sp_u, 
 {
     factor_node_steps(B, x, sp_u, outer, q, [](std::vector<Step> &, int, int) {});
 }
+
+// Diagonal-first variant for fronts that keep the outer-block inverses (x.winv >= 0, in-core schedules).  Per outer block
+// O of 512 columns: the chain of eight (left-looking update, POTRF, TRSM) triples runs on the w x w DIAGONAL block only --
+// launches of a few tiles each instead of launches as tall as the front --, the inverse Wf = L_OO^-1 is built by recursive
+// doubling (winv_doubling_steps; the Takahashi recursion and the solves reuse it), and the rows below get ONE product
+// L[B,O] = A[B,O] Wf^T with N = 512 (computed by 64-column strips into scratch `Y` of the Y space, since strip j reads
+// the strips <= j of A, then copied back).  Same flops as the blocked left-looking scheme; the dependent chain of a
+// front loses the tall skinny launches.
+static inline void factor_node_steps_diag(LevelBuilder &B, const SNode &x, int sp_u, int64_t Y, std::vector<Step> &q);
 
 static inline Step copy_step(int variant, int64_t a0, int64_t a1, int64_t host_off)
 {
@@ -589,8 +615,10 @@ static inline WtwTask winv_copy_task(const SNode &x, int k)
 // Doubling rounds inv([[A,0],[B,C]]) = [[A^-1,0],[-C^-1 B A^-1, C^-1]] of two grouped products each for the outer blocks
 // k_lo..k_hi-1 of one front (block diagonal already copied), then the seeds Z[O,O] = Wf^T Wf.  `toff` = scratch in the Y
 // space (<= 128 doubles per pivot column of the blocks treated).
-static inline void winv_doubling_steps(LevelBuilder &B, const SNode &x, int k_lo, int k_hi, int64_t toff0, int sp_z, std::vector<Step> &q)
+static inline void winv_doubling_steps(LevelBuilder &B, const SNode &x, int k_lo, int k_hi, int64_t toff0, int sp_z, std::vector<Step> &q,
+                                       bool doubling = true, bool seeds = true)
 {
+    if (doubling)
     for (int s = 1; s < SEL_OUTER; s *= 2) {
         // phase 0: T = L[C,A] Wf[A,A]      phase 1: Wf[C,A] = -Wf[C,C] T
         for (int phase = 0; phase < 2; phase++) {
@@ -618,7 +646,7 @@ static inline void winv_doubling_steps(LevelBuilder &B, const SNode &x, int k_lo
             }
         }
     }
-    for (int k = k_lo; k < k_hi; k++) {
+    for (int k = k_lo; seeds && k < k_hi; k++) {
         const OuterBlk o = outer_block(x, k);
         GemmTask t = B.task(SP_DINV, o.wf, o.ldw, SP_DINV, o.wf, o.ldw,
                             sp_z, x.front + o.c0 + (int64_t)o.c0 * x.ld, x.ld, o.w, o.w, o.w, GF_BETA0);
@@ -627,11 +655,83 @@ static inline void winv_doubling_steps(LevelBuilder &B, const SNode &x, int k_lo
     }
 }
 
+static inline void factor_node_steps_diag(LevelBuilder &B, const SNode &x, int sp_u, int64_t Y, std::vector<Step> &q)
+{
+    const int mrows = x.ncp + x.nr;
+    const int no = n_outer(x);
+    for (int k = 0; k < no; k++) {
+        const OuterBlk o = outer_block(x, k);
+        const int c0 = o.c0, w = o.w, cE = c0 + w;
+        for (int p = 0; p < o.nb; p++) {
+            const int c = c0 + p * NB, b = std::min(NB, cE - c);
+            if (p > 0)      // left-looking update of block column p, rows of the diagonal block only
+                B.add_gemm(q, B.task(SP_L, x.panel + c + (int64_t)c0 * x.ld, x.ld,
+                                     SP_L, x.panel + c + (int64_t)c0 * x.ld, x.ld,
+                                     SP_L, x.panel + c + (int64_t)c * x.ld, x.ld,
+                                     cE - c, b, c - c0, GF_NEG), false, false);
+            Step st;
+            memset(&st, 0, sizeof st);
+            st.kind = LK_POTRF;
+            st.p.blk = x.panel + c + (int64_t)c * x.ld;
+            st.p.dinv = x.dinv + (int64_t)(k * SEL_OUTER + p) * NB * NB;
+            st.p.ld = x.ld; st.p.b = b; st.p.col0 = x.first + c;
+            q.push_back(st);
+            if (cE - c - b > 0)      // rows of the diagonal block below: L = A W^T, in place
+                B.add_gemm(q, B.task(SP_L, x.panel + (c + b) + (int64_t)c * x.ld, x.ld,
+                                     SP_DINV, st.p.dinv, NB,
+                                     SP_L, x.panel + (c + b) + (int64_t)c * x.ld, x.ld,
+                                     cE - c - b, b, b, GF_BETA0), false, false);
+        }
+        // Wf = L_OO^-1
+        {
+            Step st;
+            memset(&st, 0, sizeof st);
+            st.kind = LK_WTW;
+            st.w = winv_copy_task(x, k);
+            q.push_back(st);
+            winv_doubling_steps(B, x, k, k + 1, Y, 0, q, true, false);
+        }
+        const int r0 = (k == no - 1) ? x.ncp : cE;
+        const int mb = mrows - r0;
+        if (mb > 0) {
+            // S = A[B,O] Wf^T by column strips (strip j reads the columns <= 64 (j+1) of A: Wf is lower triangular), then L[B,O] <- S
+            const int ldS = up2(mb);
+            for (int j = 0; j < o.nb; j++) {
+                const int bj = std::min(NB, w - j * NB);
+                GemmTask t = B.task(SP_L, x.panel + r0 + (int64_t)c0 * x.ld, x.ld,
+                                    SP_DINV, o.wf + j * NB, o.ldw,
+                                    SP_Y, Y + (int64_t)j * NB * ldS, ldS, mb, bj, j * NB + bj, GF_BETA0);
+                if (j == 0) B.add_gemm(q, t, false, false);
+                else B.join_gemm(q, t);
+            }
+            Step st;
+            memset(&st, 0, sizeof st);
+            st.kind = LK_BCOPY;
+            st.cp.dst = x.panel + r0 + (int64_t)c0 * x.ld; st.cp.ldd = x.ld; st.cp.dst_space = SP_L;
+            st.cp.src = Y; st.cp.lds = ldS; st.cp.src_space = SP_Y;
+            st.cp.rows = mb; st.cp.cols = w;
+            q.push_back(st);
+        }
+        if (k < no - 1) {
+            // right-looking update of the panel columns beyond this outer block
+            const int K = w;
+            B.add_gemm(q, B.task(SP_L, x.panel + cE + (int64_t)c0 * x.ld, x.ld,
+                                 SP_L, x.panel + cE + (int64_t)c0 * x.ld, x.ld,
+                                 SP_L, x.panel + cE + (int64_t)cE * x.ld, x.ld,
+                                 mrows - cE, x.nc - cE, K, GF_NEG | GF_LOWER), false, false);
+        }
+    }
+    if (x.nr > 0)
+        B.add_gemm(q, B.task(SP_L, x.panel + x.ncp, x.ld, SP_L, x.panel + x.ncp, x.ld,
+                             sp_u, x.upd, x.ldu, x.nr, x.nr, x.nc, GF_NEG | GF_LOWER), false, false);
+}
+
 // Hoisted, once per level: Wf of every outer block of the given fronts and the seeds Z[O,O] = Wf^T Wf, in seven grouped
 // launches.  `yoff[i]` = scratch of front i in the Y space.
-static inline void winv_level_launches(Program &P, const std::vector<const SNode *> &nodes, const std::vector<int64_t> &yoff, int sp_z)
+static inline void winv_level_launches(Program &P, const std::vector<const SNode *> &nodes, const std::vector<int64_t> &yoff, int sp_z,
+                                       bool from_factor = false)
 {
-    {
+    if (!from_factor) {
         Launch L;
         memset(&L, 0, sizeof L);
         L.kind = LK_WTW;
@@ -644,7 +744,7 @@ static inline void winv_level_launches(Program &P, const std::vector<const SNode
     LevelBuilder B(P);
     for (size_t fi = 0; fi < nodes.size(); fi++) {
         std::vector<Step> q;
-        winv_doubling_steps(B, *nodes[fi], 0, n_outer(*nodes[fi]), yoff[fi], sp_z, q);
+        winv_doubling_steps(B, *nodes[fi], 0, n_outer(*nodes[fi]), yoff[fi], sp_z, q, !from_factor, true);
         B.seq.push_back(std::move(q));
     }
     B.flush();
