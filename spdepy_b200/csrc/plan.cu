@@ -81,7 +81,7 @@ __global__ void k_extend_add(const ExtTask *__restrict__ tasks, const TileRef *_
 //     8x8 triangular inverses by substitution (one thread per column, column kept in registers), then three
 //     doubling levels of two small dense products each -- 7 barriers instead of a 63-step substitution.
 constexpr int POTRF_THREADS = 512;
-template <bool BENCH>
+template <bool BENCH, int SWEEP = 2>
 __global__ void __launch_bounds__(POTRF_THREADS) k_potrf_t(const PotrfTask *__restrict__ tasks, double *__restrict__ L,
                                                            double *__restrict__ dinv, int *__restrict__ status,
                                                            long long *__restrict__ clk)
@@ -104,7 +104,45 @@ __global__ void __launch_bounds__(POTRF_THREADS) k_potrf_t(const PotrfTask *__re
     }
     __syncthreads();
     POTRF_MARK(1);
-    {
+    if (SWEEP == 2) {
+        // Register-resident sweep (round 2).  Thread (row i = tid % 64, group ty = tid / 64) keeps the entries A(i, ty + 8k),
+        // k = 0..7, of its row in registers for the whole sweep.  Per column j: the owners of column j publish its current
+        // (unscaled) values to a double-buffered shared column, ONE barrier, then every thread reads the pivot and the
+        // handful of column entries it needs, forms 1/sqrt(d) itself and updates its registers -- one shared-memory round
+        // trip and one barrier on the dependent chain of a column (the shared-memory sweep below has two round trips and a
+        // two-pass update loop): ~450 instead of ~840 cycles per column (tools/potrf_probe.py).
+        constexpr int G = POTRF_THREADS / NB;       // 8 column groups
+        static_assert(G == 8 && NB == 64, "register layout of the sweep");
+        __shared__ double colbuf[2][NB];
+        const int i = tid & 63, ty = tid >> 6;
+        double r[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) { const int c = ty + G * k; r[k] = (c <= i && i < b) ? a[i][c] : 0.0; }
+#pragma unroll
+        for (int kj = 0; kj < 8; kj++) {
+#pragma unroll 1
+            for (int own = 0; own < G; own++) {
+                const int j = kj * G + own;
+                if (j >= b) break;                               // uniform per CTA
+                double *cb = colbuf[j & 1];
+                if (ty == own && i >= j) cb[i] = r[kj];
+                __syncthreads();
+                const double d = cb[j];
+                const bool ok = d > 0.0;
+                const double inv = ok ? rsqrt(d) : nan("");     // 1/l_jj
+                const double li = (i > j && i < b) ? cb[i] * inv : 0.0;
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    const int c = ty + G * k;
+                    if (c > j && c <= i) r[k] -= li * (cb[c] * inv);
+                }
+                if (ty == 0 && i > j && i < b) a[i][j] = li;
+                if (tid == 0) { a[j][j] = d * inv; wd[j] = inv; if (!ok && bad < 0) bad = j; }
+            }
+        }
+        if (tid >= b && tid < NB) wd[tid] = 0.0;
+        __syncthreads();
+    } else {
         // rows i = tid % 64; the threads of a row split its columns c = j+1+ty, +G, ... (G column groups)
         constexpr int G = POTRF_THREADS / NB;
         const int i = tid & 63, ty = tid >> 6;
@@ -367,6 +405,7 @@ __global__ void k_extract(const ZEntry *__restrict__ ent, long long a0, long lon
 // the data dependency.  Measured on B200 (C2: 38.1 ms with vs 35.2 ms without, C3: 860 vs 850 ms) the early
 // launch does not pay for these schedules, so plain stream order is the default; SPDE_PDL=1 enables it.
 static int g_pdl = 0;
+static int g_potrf_sweep = 2;      // SPDE_POTRF_SWEEP=1: the shared-memory column sweep of round 1
 template <class... KArgs, class... Args>
 static cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args)
 {
@@ -570,8 +609,12 @@ int issue_program_ex(Plan &p, Program &P, const ExecCtx &ctx, cudaStream_t st)
             else SPDE_CUDA_CHECK(launch_pdl(k_gemv_grouped<false>, dim3(L.ntiles), dim3(256), 0, st, P.d_gemm + L.task0, P.d_tiles + L.tile0, sp));
             break;
         case LK_POTRF:
-            SPDE_CUDA_CHECK(launch_pdl(k_potrf_t<false>, dim3(L.ntasks), dim3(POTRF_THREADS), 0, st, P.d_potrf + L.task0, ctx.L, ctx.dinv, ctx.status,
-                                       (long long *)nullptr));
+            if (g_potrf_sweep == 1)
+                SPDE_CUDA_CHECK(launch_pdl(k_potrf_t<false, 1>, dim3(L.ntasks), dim3(POTRF_THREADS), 0, st, P.d_potrf + L.task0, ctx.L, ctx.dinv,
+                                           ctx.status, (long long *)nullptr));
+            else
+                SPDE_CUDA_CHECK(launch_pdl(k_potrf_t<false, 2>, dim3(L.ntasks), dim3(POTRF_THREADS), 0, st, P.d_potrf + L.task0, ctx.L, ctx.dinv,
+                                           ctx.status, (long long *)nullptr));
             break;
         case LK_EXTADD:
             SPDE_CUDA_CHECK(launch_pdl(k_extend_add, dim3(L.ntiles), dim3(32, 8), 0, st, P.d_ext + L.task0, P.d_tiles + L.tile0, sp));
@@ -746,6 +789,8 @@ void init_exec_env(Plan &p)
     if (pdl) g_pdl = atoi(pdl);
     const char *ln = getenv("SPDE_LANES");
     if (ln) p.use_lanes = atoi(ln);
+    const char *ps = getenv("SPDE_POTRF_SWEEP");
+    if (ps) g_potrf_sweep = atoi(ps);
 }
 
 static int ensure_device(Plan &p, int which)
@@ -1158,9 +1203,15 @@ extern "C" int spde_potrf_bench(int b, int ld, int ntasks, int reps, float *h_us
     SPDE_CUDA_CHECK(cudaMemset(dS, 0, sizeof(int)));
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
-    k_potrf_t<true><<<ntasks, POTRF_THREADS, 0, st>>>(dT, dL, dW, dS, dC);
+    const char *psw = getenv("SPDE_POTRF_SWEEP");
+    const bool v1 = psw && atoi(psw) == 1;
+    if (v1) k_potrf_t<true, 1><<<ntasks, POTRF_THREADS, 0, st>>>(dT, dL, dW, dS, dC);
+    else k_potrf_t<true, 2><<<ntasks, POTRF_THREADS, 0, st>>>(dT, dL, dW, dS, dC);
     cudaEventRecord(e0, st);
-    for (int r = 0; r < reps; r++) k_potrf_t<true><<<ntasks, POTRF_THREADS, 0, st>>>(dT, dL, dW, dS, dC);
+    for (int r = 0; r < reps; r++) {
+        if (v1) k_potrf_t<true, 1><<<ntasks, POTRF_THREADS, 0, st>>>(dT, dL, dW, dS, dC);
+        else k_potrf_t<true, 2><<<ntasks, POTRF_THREADS, 0, st>>>(dT, dL, dW, dS, dC);
+    }
     cudaEventRecord(e1, st);
     SPDE_CUDA_CHECK(cudaStreamSynchronize(st));
     float ms = 0.f;

@@ -143,6 +143,10 @@ void Plan::build_factor_program()
     // -- every launch of the dependent chain costs ~10 us whatever its height, and the variant adds nine launches per outer
     // block (copy, six doubling products, the strip product, the copy back) to save tile rows, not launches.  Off by default.
     winv_from_factor = !lookahead && !envo && env_int("SPDE_FACTOR_DIAG", 0, 0) != 0;
+    // POTRF of a diagonal block beside the left-looking update of the rows below it (side lane), see factor_node_steps.
+    // Measured on B200 (profiles/r2_factor_diag_ab.txt): C3 factorisation 252.2 ms with vs 253.1 ms without, C2 10.30 vs 10.10 ms
+    // -- the two extra fork / join edges per 64 columns cost what the overlap gains.  Off by default.
+    const bool potrf_overlap = !lookahead && env_int("SPDE_POTRF_OVERLAP", 0, 0) != 0;
     // The update-matrix arena of level d-1 is the arena the extend-add of level d has just consumed, so it is zeroed on the
     // side lane under the (compute-bound) factorisation of level d instead of in front of level d-1: LK_SYNC records fork
     // and join the lane; executors without lanes run the list in order, which is just as valid.
@@ -304,7 +308,7 @@ void Plan::build_factor_program()
         for (int s : lev) {
             std::vector<Step> q;
             if (winv_from_factor && sn[s].winv >= 0) factor_node_steps_diag(B, sn[s], sp_u, yoff, q);
-            else factor_node_steps(B, sn[s], sp_u, OUTER, q);
+            else factor_node_steps(B, sn[s], sp_u, OUTER, q, potrf_overlap);
             yoff += sn[s].winv >= 0 ? ybuf_need(sn[s]) : (int64_t)sn[s].ld * NB;
             B.seq.push_back(std::move(q));
         }

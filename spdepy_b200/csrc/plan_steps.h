@@ -45,6 +45,7 @@ struct Step {
     WtwTask w;
     CopyTask cp;
     Launch raw;          // LK_COPY: the launch record itself
+    int lane;            // 0 = main lane, 1 = side lane (GEMM steps); LK_SYNC: event number
 };
 
 struct LevelBuilder {
@@ -75,6 +76,15 @@ struct LevelBuilder {
         st.g0 = (int)pool.size();
         st.gn = 1;
         pool.push_back(t);
+        s.push_back(st);
+    }
+    // lane fork / join record as a step (see LK_SYNC in plan.h): 0 = side lane waits for the main lane, 1 = record event
+    // `ev` on the side lane, 2 = main lane waits for event `ev`
+    void add_sync(std::vector<Step> &s, int variant, int ev)
+    {
+        Step st;
+        memset(&st, 0, sizeof st);
+        st.kind = LK_SYNC; st.variant = variant; st.lane = ev;
         s.push_back(st);
     }
     // small-M (k <= 4 right-hand sides) matrix-vector step; variant = B layout
@@ -203,9 +213,14 @@ struct LevelBuilder {
         for (auto &s : seq) remaining += s.size();
         while (remaining) {
             // pick the (kind, variant) shared by most heads
+            // (GEMM steps: same variant and same lane; lane fork / join records: same kind of record and same event)
+            auto subkey = [](const Step &st) {
+                if (st.kind == LK_GEMM || st.kind == LK_GEMV || st.kind == LK_SYNC) return st.variant | (st.lane << 16);
+                return 0;
+            };
             std::map<std::pair<int, int>, int> votes;
             for (size_t i = 0; i < m; i++)
-                if (head[i] < seq[i].size()) votes[{seq[i][head[i]].kind, (seq[i][head[i]].kind == LK_GEMM || seq[i][head[i]].kind == LK_GEMV) ? seq[i][head[i]].variant : 0}]++;
+                if (head[i] < seq[i].size()) votes[{seq[i][head[i]].kind, subkey(seq[i][head[i]])}]++;
             std::pair<int, int> best{-1, -1};
             int bv = -1;
             for (auto &kv : votes) if (kv.second > bv) { bv = kv.second; best = kv.first; }
@@ -213,14 +228,21 @@ struct LevelBuilder {
             for (size_t i = 0; i < m; i++) {
                 if (head[i] >= seq[i].size()) continue;
                 const Step &st = seq[i][head[i]];
-                if (st.kind != best.first) continue;
-                if ((st.kind == LK_GEMM || st.kind == LK_GEMV) && st.variant != best.second) continue;
+                if (st.kind != best.first || subkey(st) != best.second) continue;
                 chosen.push_back(&st);
                 head[i]++;
                 remaining--;
             }
             if (best.first == LK_GEMM) {
-                emit_gemm_launch(best.second, chosen);
+                const size_t from = prog.launches.size();
+                emit_gemm_launch(best.second & 0xffff, chosen);
+                for (size_t i = from; i < prog.launches.size(); i++) prog.launches[i].lane = best.second >> 16;
+            } else if (best.first == LK_SYNC) {
+                // the records are global orderings between the two lanes, so one record serves every front at this step
+                Launch L;
+                memset(&L, 0, sizeof L);
+                L.kind = LK_SYNC; L.variant = best.second & 0xffff; L.a0 = best.second >> 16;
+                prog.launches.push_back(L);
             } else if (best.first == LK_GEMV) {
                 emit_gemv_launch(best.second, chosen);
             } else if (best.first == LK_POTRF) {
@@ -322,8 +344,12 @@ static inline void push_gather_task(Program &P, Launch &L, long long dst, int ld
 // `outer` 64-column blocks, 64x64 POTRF with explicit inverse, TRSM-as-GEMM with that inverse, right-looking GEMM
 // beyond the outer block, one SYRK of the update matrix with K = all pivot columns.
 // `after_outer(q, P0, P1)` (optional) is called when the block columns P0..P1-1 hold their final values.
+// `potrf_overlap`: the left-looking update of block column p is split into its diagonal tile (main lane, what POTRF
+// needs) and the rows below (side lane), so that the 41 us POTRF of the diagonal block runs beside the update of the rows
+// below instead of after it; the two meet again in front of the TRSM.  Same arithmetic, same results.
 template <class Hook>
-static inline void factor_node_steps(LevelBuilder &B, const SNode &x, int sp_u, int outer, std::vector<Step> &q, Hook after_outer)
+static inline void factor_node_steps(LevelBuilder &B, const SNode &x, int sp_u, int outer, std::vector<Step> &q, Hook after_outer,
+                                     bool potrf_overlap = false)
 {
     const int mrows = x.ncp + x.nr;     // panel rows in use (the gap row of an odd nc is zero)
     for (int P0 = 0; P0 < x.nblk; P0 += outer) {
@@ -331,13 +357,31 @@ static inline void factor_node_steps(LevelBuilder &B, const SNode &x, int sp_u, 
         const int cP = P0 * NB;
         for (int p = P0; p < P1; p++) {
             const int c0 = p * NB, b = std::min(NB, x.nc - c0);
+            bool forked = false;
             if (p > P0) {
                 // left-looking update of block column p from the inner blocks of this outer block
                 const int K = c0 - cP;
-                B.add_gemm(q, B.task(SP_L, x.panel + c0 + (int64_t)cP * x.ld, x.ld,
-                                     SP_L, x.panel + c0 + (int64_t)cP * x.ld, x.ld,
-                                     SP_L, x.panel + c0 + (int64_t)c0 * x.ld, x.ld,
-                                     mrows - c0, b, K, GF_NEG), false, false);
+                const int rb = (p == x.nblk - 1) ? x.ncp : c0 + NB;      // first row below the diagonal block (even: tile alignment)
+                const int below = mrows - rb;
+                if (potrf_overlap && below >= 4 * NB) {
+                    B.add_sync(q, 0, 0);
+                    B.add_gemm(q, B.task(SP_L, x.panel + rb + (int64_t)cP * x.ld, x.ld,
+                                         SP_L, x.panel + c0 + (int64_t)cP * x.ld, x.ld,
+                                         SP_L, x.panel + rb + (int64_t)c0 * x.ld, x.ld,
+                                         below, b, K, GF_NEG), false, false);
+                    q.back().lane = 1;
+                    B.add_sync(q, 1, p & 1);
+                    B.add_gemm(q, B.task(SP_L, x.panel + c0 + (int64_t)cP * x.ld, x.ld,
+                                         SP_L, x.panel + c0 + (int64_t)cP * x.ld, x.ld,
+                                         SP_L, x.panel + c0 + (int64_t)c0 * x.ld, x.ld,
+                                         b, b, K, GF_NEG), false, false);
+                    forked = true;
+                } else {
+                    B.add_gemm(q, B.task(SP_L, x.panel + c0 + (int64_t)cP * x.ld, x.ld,
+                                         SP_L, x.panel + c0 + (int64_t)cP * x.ld, x.ld,
+                                         SP_L, x.panel + c0 + (int64_t)c0 * x.ld, x.ld,
+                                         mrows - c0, b, K, GF_NEG), false, false);
+                }
             }
             Step st;
             memset(&st, 0, sizeof st);
@@ -346,6 +390,7 @@ static inline void factor_node_steps(LevelBuilder &B, const SNode &x, int sp_u, 
             st.p.dinv = x.dinv + (int64_t)p * NB * NB;
             st.p.ld = x.ld; st.p.b = b; st.p.col0 = x.first + c0;
             q.push_back(st);
+            if (forked) B.add_sync(q, 2, p & 1);
             // rows below the diagonal block: L = A * W^T, in place
             const int r0 = (p == x.nblk - 1) ? x.ncp : c0 + NB;
             B.add_gemm(q, B.task(SP_L, x.panel + r0 + (int64_t)c0 * x.ld, x.ld,
@@ -370,9 +415,9 @@ static inline void factor_node_steps(LevelBuilder &B, const SNode &x, int sp_u, 
     }
 }
 
-static inline void factor_node_steps(LevelBuilder &B, const SNode &x, int sp_u, int outer, std::vector<Step> &q)
+static inline void factor_node_steps(LevelBuilder &B, const SNode &x, int sp_u, int outer, std::vector<Step> &q, bool potrf_overlap = false)
 {
-    factor_node_steps(B, x, sp_u, outer, q, [](std::vector<Step> &, int, int) {});
+    factor_node_steps(B, x, sp_u, outer, q, [](std::vector<Step> &, int, int) {}, potrf_overlap);
 }
 
 // Diagonal-first variant for fronts that keep the outer-block inverses (x.winv >= 0, in-core schedules).  Per outer block

@@ -184,6 +184,28 @@ def test_emulated_selinv_outer_blocks(monkeypatch, blocks, kchunk2, diag):
     assert np.abs(Z0 - Zq).max() < 1e-11 * np.abs(Zd).max()
 
 
+def test_emulated_potrf_overlap_schedule(monkeypatch):
+    """Opt-in factor schedule with the left-looking update split into its diagonal tile (main lane) and the rows below
+    (side lane, LK_SYNC fork / join records): the launch list stays a valid serial order and gives the same factor."""
+    M, N, T, bc = 24, 22, 9, 3
+    pat = Pattern(M, N, T, bc)
+    rng = np.random.default_rng(5)
+    plan0 = _lib.PlanHandle(M, N, T, bc)
+    n = plan0.n
+    W = pat.to_csc(rng.normal(size=pat.nslots * n))
+    A = (W + W.T) * 0.5
+    A = sparse.csc_matrix(A + sparse.diags(np.abs(A).sum(axis=1).A1 + 1.0))
+    em0 = pe.Emulator(plan0)
+    assert em0.factorize(pat.from_sparse(A)) == 0
+    monkeypatch.setenv("SPDE_POTRF_OVERLAP", "1")
+    plan1 = _lib.PlanHandle(M, N, T, bc)
+    L1 = pe.Program(plan1, 0).launches
+    assert ((L1["kind"] == pe.LK_SYNC) & (L1["variant"] == 1)).sum() > 0 and (L1["lane"] == 1).sum() > 0
+    em1 = pe.Emulator(plan1)
+    assert em1.factorize(pat.from_sparse(A)) == 0
+    assert np.abs(em1.sp[0] - em0.sp[0]).max() <= 1e-13 * np.abs(em0.sp[0]).max()
+
+
 def test_emulated_selinv_split_k(monkeypatch):
     """The split-K variant of the skinny Takahashi product (normally only for fronts >= 2048 rows)."""
     monkeypatch.setenv("SPDE_SPLITK_MIN", "64")
