@@ -768,8 +768,13 @@ extern "C" int spde_ooc_run(spde_ooc *oo, const double *d_Q, const double *d_cnt
     ctx.h_pool = backward ? o.h_pool : nullptr;
     ctx.copy_stream = o.copy_stream; ctx.copy_fork = o.copy_fork; ctx.fetch_ev = &o.fetch_ev;
     const cudaStream_t cs = p.prof_on ? st : o.copy_stream;     // profiled evaluations keep everything on one stream
-    cudaEvent_t ev[3];
-    for (auto &e : ev) SPDE_CUDA_CHECK(cudaEventCreate(&e));
+    // pass-boundary events, destroyed on every exit path (the error returns below included)
+    struct PassEvents {
+        cudaEvent_t e[3] = {nullptr, nullptr, nullptr};
+        ~PassEvents() { for (auto &x : e) if (x) cudaEventDestroy(x); }
+    } pev;
+    cudaEvent_t *ev = pev.e;
+    for (int i = 0; i < 3; i++) SPDE_CUDA_CHECK(cudaEventCreate(&ev[i]));
     SPDE_CUDA_CHECK(cudaMemsetAsync(o.d_status, 0, sizeof(int), st));
     if (k > 0) { rc = launch_perm_in(d_X, o.d_perm, n, k, kp, (mode >> 2) & 1, o.d_Xp, st); if (rc) return rc; }
     SPDE_CUDA_CHECK(cudaEventRecord(ev[0], st));
@@ -881,7 +886,6 @@ extern "C" int spde_ooc_run(spde_ooc *oo, const double *d_Q, const double *d_cnt
     float ms = 0.f;
     cudaEventElapsedTime(&ms, ev[0], ev[1]); o.last_ms[0] = ms;
     cudaEventElapsedTime(&ms, ev[1], ev[2]); o.last_ms[1] = ms;
-    for (auto &e : ev) cudaEventDestroy(e);
     double sum = 0.0;
     for (int i : o.order) sum += ld[i];       // fixed order
     o.last_ld = ld;

@@ -428,11 +428,14 @@ static cudaError_t launch_gemm_variant(const Launch &L, const Program &P, const 
 {
     auto kern = k_gemm_grouped<BM, BN, WMn, WNn, AK, BK_, BKT, STG>;
     constexpr int smem = gemm_smem_bytes<BM, BN, BKT, STG>();
-    static bool attr_done = false;
-    if (!attr_done) {
+    static bool attr_done[64] = {false};      // function attributes are per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dev &= 63;
+    if (!attr_done[dev]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;
-        attr_done = true;
+        attr_done[dev] = true;
     }
     return launch_pdl(kern, dim3(L.ntiles), dim3(WMn * WNn * 32), smem, st, P.d_gemm + L.task0, P.d_tiles + L.tile0, sp);
 }
@@ -453,11 +456,14 @@ static cudaError_t launch_gemm(const Launch &L, const Program &P, const GemmSpac
     // tuning-only tile shapes (NT layout), reachable through spde_gemm_single
     if (ak == 0 && bk == 0) {
         if (cfg == 3) {     // warp-specialised bulk-async kernel (k_gemm_ws): the production kernel of the N/N layout
-            static bool ws_attr = false;
-            if (!ws_attr) {
+            static bool ws_attr[64] = {false};
+            int dev = 0;
+            cudaGetDevice(&dev);
+            dev &= 63;
+            if (!ws_attr[dev]) {
                 cudaError_t e = cudaFuncSetAttribute(k_gemm_ws<WS_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_ws_smem_bytes());
                 if (e != cudaSuccess) return e;
-                ws_attr = true;
+                ws_attr[dev] = true;
             }
             return launch_pdl(k_gemm_ws<WS_STAGES>, dim3(L.ntiles), dim3(WS_THREADS), (size_t)gemm_ws_smem_bytes(), st,
                               P.d_gemm + L.task0, P.d_tiles + L.tile0, sp);
@@ -690,9 +696,12 @@ void init_exec_env(Plan &p);
 
 static void init_gemm_attributes()
 {
-    static bool done = false;
-    if (done) return;
-    done = true;
+    static bool done[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dev &= 63;
+    if (done[dev]) return;
+    done[dev] = true;
 #define A(BM, BN, WM, WN)                                                                                          \
     cudaFuncSetAttribute(k_gemm_grouped<BM, BN, WM, WN, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes<BM, BN>()); \
     cudaFuncSetAttribute(k_gemm_grouped<BM, BN, WM, WN, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes<BM, BN>());  \

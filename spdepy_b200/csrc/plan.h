@@ -99,7 +99,9 @@ struct Plan {
     std::map<std::pair<int, int>, Program> solve;   // (k, direction) -> program
     Program selinv;
     bool selinv_built = false;
-    bool winv_from_factor = false;   // the factorisation leaves the outer-block inverses Wf behind (diagonal-first panels)
+    bool winv_from_factor = false;   // the factorisation leaves the outer-block inverses Wf behind (diagonal-first panels) ...
+    int diag_min_ld = 0;             // ... on the fronts with at least this many rows
+    bool diag_front(const SNode &x) const { return winv_from_factor && x.winv >= 0 && x.ld >= diag_min_ld; }
     // device state
     int device_ready = 0;
     double *d_L[2] = {nullptr, nullptr};

@@ -143,6 +143,7 @@ void Plan::build_factor_program()
     // -- every launch of the dependent chain costs ~10 us whatever its height, and the variant adds nine launches per outer
     // block (copy, six doubling products, the strip product, the copy back) to save tile rows, not launches.  Off by default.
     winv_from_factor = !lookahead && !envo && env_int("SPDE_FACTOR_DIAG", 0, 0) != 0;
+    diag_min_ld = env_int("SPDE_FACTOR_DIAG_MIN", 0, 0);      // only fronts at least this tall (their chain launches are the long ones)
     // POTRF of a diagonal block beside the left-looking update of the rows below it (side lane), see factor_node_steps.
     // Measured on B200 (profiles/r2_factor_diag_ab.txt): C3 factorisation 252.2 ms with vs 253.1 ms without, C2 10.30 vs 10.10 ms
     // -- the two extra fork / join edges per 64 columns cost what the overlap gains.  Off by default.
@@ -307,7 +308,7 @@ void Plan::build_factor_program()
         int64_t yoff = 0;
         for (int s : lev) {
             std::vector<Step> q;
-            if (winv_from_factor && sn[s].winv >= 0) factor_node_steps_diag(B, sn[s], sp_u, yoff, q);
+            if (diag_front(sn[s])) factor_node_steps_diag(B, sn[s], sp_u, yoff, q);
             else factor_node_steps(B, sn[s], sp_u, OUTER, q, potrf_overlap);
             yoff += sn[s].winv >= 0 ? ybuf_need(sn[s]) : (int64_t)sn[s].ld * NB;
             B.seq.push_back(std::move(q));
@@ -419,16 +420,18 @@ void Plan::build_selinv_program()
         // inverses Wf and Wf^T Wf of the others in seven grouped launches
         std::vector<int64_t> yoffs;
         {
-            std::vector<const SNode *> single, multi;
-            std::vector<int64_t> ymulti;
+            std::vector<const SNode *> single, multi, multi_f;
+            std::vector<int64_t> ymulti, ymulti_f;
             int64_t yoff = 0;
             for (int s : lev) {
                 yoffs.push_back(yoff);
-                if (sn[s].winv >= 0) { multi.push_back(&sn[s]); ymulti.push_back(yoff); yoff += ybuf_need(sn[s]); }
+                if (diag_front(sn[s])) { multi_f.push_back(&sn[s]); ymulti_f.push_back(yoff); yoff += ybuf_need(sn[s]); }
+                else if (sn[s].winv >= 0) { multi.push_back(&sn[s]); ymulti.push_back(yoff); yoff += ybuf_need(sn[s]); }
                 else { single.push_back(&sn[s]); yoff += (int64_t)sn[s].ld * NB; }
             }
             wtw_level_launch(P, single, sp_z);
-            if (!multi.empty()) winv_level_launches(P, multi, ymulti, sp_z, winv_from_factor);
+            if (!multi.empty()) winv_level_launches(P, multi, ymulti, sp_z, false);
+            if (!multi_f.empty()) winv_level_launches(P, multi_f, ymulti_f, sp_z, true);     // (Wf left behind by the factorisation)
         }
         LevelBuilder B(P);
         for (size_t i = 0; i < lev.size(); i++) {

@@ -321,10 +321,18 @@ __global__ void k_gemv_final(const double *__restrict__ partial, int nb, double 
     if (threadIdx.x == 0) out[blockIdx.x] = s;
 }
 
-static double *g_scratch = nullptr;   // 64 KiB of device scratch for the reductions
+// 64 KiB of device scratch for the reductions, one per device (a process may drive several GPUs: Engine caches one
+// engine per device); g_scratch is the scratch of the CURRENT device, selected by ensure_scratch() on every entry
+constexpr int kMaxDevices = 64;
+static double *g_scratch_of[kMaxDevices] = {nullptr};
+static thread_local double *g_scratch = nullptr;
 static int ensure_scratch()
 {
-    if (!g_scratch) SPDE_CUDA_CHECK(cudaMalloc((void **)&g_scratch, 8192 * sizeof(double)));
+    int dev = 0;
+    SPDE_CUDA_CHECK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= kMaxDevices) { set_error("more than 64 devices"); return SPDE_ERR_ARG; }
+    if (!g_scratch_of[dev]) SPDE_CUDA_CHECK(cudaMalloc((void **)&g_scratch_of[dev], 8192 * sizeof(double)));
+    g_scratch = g_scratch_of[dev];
     return SPDE_OK;
 }
 
