@@ -298,6 +298,7 @@ class Engine:
         check(lib.spde_factorize_async(self.plan.h, which, ptr(Q), ptr(cnt), float(tau), _stream()))
 
     def factor_wait(self, which: int) -> Factor:
+        COUNTERS["d2h"] += 4          # the positive-definiteness status word
         check(lib.spde_factor_wait(self.plan.h, which, _stream()))
         return Factor(self, which)
 

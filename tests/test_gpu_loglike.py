@@ -121,6 +121,29 @@ def test_exact_gradient_vs_oracle_dense_inverse(name):
     assert np.abs(jac - jac_o).max() <= 1e-9 * np.abs(jac_o).max(), (jac, jac_o)
 
 
+@pytest.mark.parametrize("name", ["ad_ani_bc3_q0", "vavd_ani_bc3", "wm_iso_bc3"])
+def test_device_resident_scalars_read_once(name):
+    """The scalars of one logLike are collected on the device and read back in ONE copy (engine.ScalarPool): the
+    device-to-host traffic of an evaluation is the pool (a few hundred doubles) plus the three factorisation status words,
+    and the result equals the eager path (every reduction copied and synchronised on its own) to the last bit or two."""
+    from spdepy_b200.engine import COUNTERS
+    d = load_golden(name)
+    mod = _build(d)
+    m = mod.mod
+    m.initFit(d["data"], idx=d["idx"], fitQ0=d["fitQ0"])
+    m.logLike(d["par"], grad=True, exact_grad=True)               # warm-up (schedules, graphs)
+    COUNTERS["d2h"] = 0
+    like, jac = m.logLike(d["par"], grad=True, exact_grad=True)
+    lazy_bytes = COUNTERS["d2h"]
+    assert lazy_bytes <= 8 * (d["par"].size + 64)
+    COUNTERS["d2h"] = 0
+    m._pool = None
+    like_e, jac_e = m._logLike(d["par"], 100, True, None, True)   # eager: host floats from every reduction
+    assert COUNTERS["d2h"] >= 8 * 8
+    assert like == pytest.approx(like_e, rel=1e-13)
+    assert np.abs(jac - jac_e).max() <= 1e-12 * np.abs(jac_e).max()
+
+
 def test_not_positive_definite_raises():
     import spdepy_b200 as sp
     from spdepy_b200._lib import NotPositiveDefiniteError
