@@ -65,7 +65,8 @@ class Emulator:
         self.n = plan.n
         self.nslots = plan.nslots
         sizes = plan.export(4, 0, "i8")
-        (self.l_size, self.dinv_size, a0, a1, z0, z1, self.ybuf_size, self.rel_base) = [int(v) for v in sizes]
+        (self.l_size, self.dinv_size, a0, a1, z0, z1, self.ybuf_size, self.rel_base) = [int(v) for v in sizes[:8]]
+        self.solve_outer = bool(sizes[8]) if len(sizes) > 8 else False      # solves ping-pong between X and X2 (space 1)
         self.qdest = plan.export(4, 1, "i8")
         self.cand = plan.export(4, 2, "i4")
         self.diagpos = plan.export(4, 3, "i8")
@@ -278,12 +279,22 @@ class Emulator:
         kp = k + (k & 1)
         Xp = np.zeros((self.n, kp))
         Xp[:, :k] = X[self.perm] if mode & 4 else X
-        self.sp[4] = Xp.reshape(-1).copy()
+        arena0 = self.sp[1]
+        if self.solve_outer:
+            # spde_solve: space 1 is the second right-hand-side buffer; forward reads X and leaves y in X2, backward reads
+            # y from X2 and leaves x in X (stale NaNs where the schedule must not read)
+            self.sp[4] = np.full(self.n * kp, np.nan)
+            self.sp[1] = np.full(self.n * kp, np.nan)
+            self.sp[4 if mode & 1 else 1] = Xp.reshape(-1).copy()
+        else:
+            self.sp[4] = Xp.reshape(-1).copy()
         if mode & 1:
             self.run(Program(self.plan, 1, k))
         if mode & 2:
             self.run(Program(self.plan, 2, k))
-        Xp = self.sp[4].reshape(self.n, kp)[:, :k]
+        res = self.sp[1 if (self.solve_outer and not mode & 2) else 4]
+        self.sp[1] = arena0
+        Xp = res.reshape(self.n, kp)[:, :k]
         out = np.empty_like(Xp)
         if mode & 8:
             out[self.perm] = Xp

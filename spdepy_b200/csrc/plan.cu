@@ -514,11 +514,13 @@ static void free_program(Program &P)
     P.uploaded = false;
 }
 
-static GemmSpaces spaces_of(Plan &p, int which)
+// (solve programs of a plan with outer-block solves: operand space 1 is the second right-hand-side buffer X2 instead of
+// the update-matrix arena, which only the factorisation uses)
+static GemmSpaces spaces_of(Plan &p, int which, bool solve = false)
 {
     GemmSpaces sp;
     sp.base[0] = p.d_L[which];
-    sp.base[1] = p.d_arena[which][0];
+    sp.base[1] = (solve && p.solve_outer) ? p.d_X2 : p.d_arena[which][0];
     sp.base[2] = p.d_arena[which][1];
     sp.base[3] = p.d_dinv[which];
     sp.base[4] = p.d_X;
@@ -534,7 +536,7 @@ static int issue_program(Plan &p, Program &P, int which, cudaStream_t st, double
     int rc = upload_program(P);
     if (rc) return rc;
     ExecCtx ctx;
-    ctx.sp = spaces_of(p, which);
+    ctx.sp = spaces_of(p, which, &P != &p.factor && &P != &p.selinv);
     ctx.L = p.d_L[which]; ctx.dinv = p.d_dinv[which]; ctx.status = p.d_status + which;
     ctx.zent = p.d_zentries; ctx.Zq = d_Zq; ctx.which = which; ctx.lanes = true;
     return issue_program_ex(p, P, ctx, st);
@@ -734,7 +736,7 @@ static int run_program(Plan &p, Program &P, int which, cudaStream_t st, double *
     if (lane == 0 || !p.pending_readonly[which]) rc = join_store(p, which, st);
     if (rc) return rc;
     if (p.prof_on || !p.use_graphs) return issue_program(p, P, which, st, d_Zq);
-    GemmSpaces sp = spaces_of(p, which);
+    GemmSpaces sp = spaces_of(p, which, &P != &p.factor && &P != &p.selinv);
     unsigned long long key = 1469598103934665603ull;
     for (int i = 0; i < 8; i++) key = (key ^ (unsigned long long)(uintptr_t)sp.base[i]) * 1099511628211ull;
     key = (key ^ (unsigned long long)(uintptr_t)d_Zq) * 1099511628211ull;
@@ -873,7 +875,7 @@ extern "C" void spde_plan_destroy(spde_plan *pp)
         }
         if (p->solve_stream[a]) { cudaStreamDestroy(p->solve_stream[a]); cudaEventDestroy(p->sev_in[a]); cudaEventDestroy(p->sev_out[a]); }
     }
-    cudaFree(p->d_X); cudaFree(p->d_red); cudaFree(p->d_idx); cudaFree(p->d_qdest);
+    cudaFree(p->d_X); cudaFree(p->d_X2); cudaFree(p->d_red); cudaFree(p->d_idx); cudaFree(p->d_qdest);
     cudaFree(p->d_diagpos); cudaFree(p->d_cand); cudaFree(p->d_perm); cudaFree(p->d_status); cudaFree(p->d_zentries);
     free_program(p->factor);
     free_program(p->selinv);
@@ -956,7 +958,8 @@ extern "C" int spde_plan_export(spde_plan *pp, int prog, int k, int what, void *
         static std::vector<int64_t> sizes;
         static std::vector<int> idx;
         switch (what) {
-        case 0: sizes = {p.l_size, p.dinv_size, p.arena_size[0], p.arena_size[1], p.zarena_size[0], p.zarena_size[1], p.ybuf_size, p.rel_base};
+        case 0: sizes = {p.l_size, p.dinv_size, p.arena_size[0], p.arena_size[1], p.zarena_size[0], p.zarena_size[1], p.ybuf_size, p.rel_base,
+                         (int64_t)p.solve_outer};
                 EXP(sizes) break;
         case 1: EXP(p.qdest) break;
         case 2: EXP(p.cand_slots) break;
@@ -1078,19 +1081,26 @@ extern "C" int spde_solve(spde_plan *pp, int which, int mode, double *d_X, int k
     const int64_t need = (int64_t)n * kp;
     if (p.x_cap < need) {
         cudaFree(p.d_X);
-        p.d_X = nullptr;
+        cudaFree(p.d_X2);
+        p.d_X = p.d_X2 = nullptr;
         p.x_cap = 0;
         SPDE_CUDA_CHECK(cudaMalloc((void **)&p.d_X, need * sizeof(double)));
+        if (p.solve_outer) SPDE_CUDA_CHECK(cudaMalloc((void **)&p.d_X2, need * sizeof(double)));
         p.x_cap = need;
     }
     const int grid = 148 * 8;
     count_launch(2);
-    k_perm_in<<<grid, 256, 0, st>>>(d_X, p.d_perm, n, k, kp, (mode >> 2) & 1, p.d_X);
+    // outer-block solves ping-pong between X and X2: the forward pass reads b from X and leaves y in X2, the backward
+    // pass reads y from X2 and leaves x in X
+    const bool pp2 = p.solve_outer;
+    double *in = (pp2 && !(mode & 1)) ? p.d_X2 : p.d_X;           // backward only: the input is y
+    double *out = (pp2 && !(mode & 2)) ? p.d_X2 : p.d_X;          // forward only: the output is y
+    k_perm_in<<<grid, 256, 0, st>>>(d_X, p.d_perm, n, k, kp, (mode >> 2) & 1, in);
     SPDE_LAUNCH_CHECK();
     int rc;
     if (mode & 1) { rc = run_program(p, p.solve_program(k, 0), which, st, nullptr, false, 1); if (rc) return rc; }
     if (mode & 2) { rc = run_program(p, p.solve_program(k, 1), which, st, nullptr, false, 1); if (rc) return rc; }
-    k_perm_out<<<grid, 256, 0, st>>>(p.d_X, p.d_perm, n, k, kp, (mode >> 3) & 1, d_X);
+    k_perm_out<<<grid, 256, 0, st>>>(out, p.d_perm, n, k, kp, (mode >> 3) & 1, d_X);
     SPDE_LAUNCH_CHECK();
     return SPDE_OK;
 }

@@ -101,6 +101,8 @@ struct Plan {
     bool selinv_built = false;
     bool winv_from_factor = false;   // the factorisation leaves the outer-block inverses Wf behind (diagonal-first panels) ...
     int diag_min_ld = 0;             // ... on the fronts with at least this many rows
+    bool solve_outer = false;        // the factor schedule ends by building Wf of every multi-block front, and the solve
+                                     // schedules work on outer blocks with two right-hand-side buffers (plan_steps.h)
     bool diag_front(const SNode &x) const { return winv_from_factor && x.winv >= 0 && x.ld >= diag_min_ld; }
     // device state
     int device_ready = 0;
@@ -110,7 +112,7 @@ struct Plan {
     double *d_arena[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
     double *d_zarena[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
     double *d_ybuf[2] = {nullptr, nullptr};
-    double *d_X = nullptr, *d_red = nullptr;
+    double *d_X = nullptr, *d_X2 = nullptr, *d_red = nullptr;
     int64_t x_cap = 0;
     int *d_idx = nullptr;          // rows | relidx
     int64_t rel_base = 0;

@@ -56,6 +56,7 @@ void Plan::build_layout()
     }
     arena_size[0] = arena_size[1] = zarena_size[0] = zarena_size[1] = 0;
     ybuf_size = 0;
+    for (int s = 0; s < ns; s++) ybuf_size += winv_scratch(sn[s]);      // doubling scratch of all fronts at once (factor epilogue)
     for (int d = 0; d <= S.maxdepth; d++) {
         arena_size[d & 1] = std::max(arena_size[d & 1], upd_used[d]);
         zarena_size[d & 1] = std::max(zarena_size[d & 1], front_used[d]);
@@ -315,6 +316,20 @@ void Plan::build_factor_program()
         }
         B.flush();
     }
+    // Epilogue: the outer-block inverses Wf of every multi-block front that did not build them on the way (seven grouped
+    // launches for the whole tree: they depend on nothing but the finished panels).  The Takahashi recursion and the
+    // triangular solves work on them.
+    solve_outer = env_int("SPDE_SOLVE_OUTER_BLOCKS", 1, 0) != 0 && !getenv("SPDE_SOLVE_OUTER");
+    for (int s = 0; s < S.nsuper; s++)
+        if (sn[s].nblk > 1 && sn[s].winv < 0) solve_outer = false;      // (SPDE_SELINV_OUTER=0: no outer-block inverses anywhere)
+    if (solve_outer) {
+        std::vector<const SNode *> nodes;
+        std::vector<int64_t> toffs;
+        int64_t toff = 0;
+        for (int s = 0; s < S.nsuper; s++)
+            if (sn[s].winv >= 0 && !diag_front(sn[s])) { nodes.push_back(&sn[s]); toffs.push_back(toff); toff += winv_scratch(sn[s]); }
+        if (!nodes.empty()) winv_level_launches(P, nodes, toffs, 0, false, false);
+    }
 }
 
 // direction 0: forward (L y = b), 1: backward (L^T x = y)
@@ -329,7 +344,28 @@ Program &Plan::solve_program(int k, int dir)
     const bool blocked = k > 4;          // tensor-core path (see add_solve)
     const char *envo = getenv("SPDE_SOLVE_OUTER");     // test hook: exercise the outer-block path on small meshes
     const int OUTER = envo ? std::max(1, atoi(envo)) : spde::OUTER;
-    if (dir == 0) {
+    if (solve_outer && dir == 0) {
+        zero_launch(P, SP_X2, 0, (int64_t)kp * S.n);
+        for (int d = S.maxdepth; d >= 0; d--) {
+            LevelBuilder B(P);
+            for (int s : by_depth[d]) {
+                std::vector<Step> q;
+                fsolve_node_steps_outer(B, sn[s], k, kp, q);
+                B.seq.push_back(std::move(q));
+            }
+            B.flush();
+        }
+    } else if (solve_outer) {
+        for (int d = 0; d <= S.maxdepth; d++) {
+            LevelBuilder B(P);
+            for (int s : by_depth[d]) {
+                std::vector<Step> q;
+                bsolve_node_steps_outer(B, sn[s], k, kp, q);
+                B.seq.push_back(std::move(q));
+            }
+            B.flush();
+        }
+    } else if (dir == 0) {
         for (int d = S.maxdepth; d >= 0; d--) {
             LevelBuilder B(P);
             for (int s : by_depth[d]) {
@@ -425,7 +461,7 @@ void Plan::build_selinv_program()
             int64_t yoff = 0;
             for (int s : lev) {
                 yoffs.push_back(yoff);
-                if (diag_front(sn[s])) { multi_f.push_back(&sn[s]); ymulti_f.push_back(yoff); yoff += ybuf_need(sn[s]); }
+                if (sn[s].winv >= 0 && (solve_outer || diag_front(sn[s]))) { multi_f.push_back(&sn[s]); ymulti_f.push_back(yoff); yoff += ybuf_need(sn[s]); }
                 else if (sn[s].winv >= 0) { multi.push_back(&sn[s]); ymulti.push_back(yoff); yoff += ybuf_need(sn[s]); }
                 else { single.push_back(&sn[s]); yoff += (int64_t)sn[s].ld * NB; }
             }

@@ -771,10 +771,77 @@ static inline void factor_node_steps_diag(LevelBuilder &B, const SNode &x, int s
                              sp_u, x.upd, x.ldu, x.nr, x.nr, x.nc, GF_NEG | GF_LOWER), false, false);
 }
 
+static inline int64_t winv_scratch(const SNode &x)      // doubling scratch of one front (doubles), see winv_doubling_steps
+{
+    return x.winv >= 0 ? (int64_t)n_outer(x) * ((int64_t)SEL_W * SEL_W / 4 + SEL_W) : 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Triangular solves on the outer-block inverses (in-core schedules of a plan whose factorisation leaves Wf behind).
+// The right-hand sides ping-pong between two buffers, X (space SP_X) and X2 (space SP_X2, which the executor maps to a
+// second k x n buffer for solve programs): a product with a 512 x 512 inverse cannot run in place, and with two buffers
+// no step reads what a concurrent tile of the same launch writes.
+//   forward  (L y = b):   b in X, y accumulates in X2 (zeroed by the program's first launch).  Per outer block O:
+//                         X2_O += X_O Wf^T;  X_later -= X2_O L[later,O]^T;  at the end of the front the rows below
+//                         receive X[rows] -= X2_front L[below,front]^T (atomic scatter, as before).
+//   backward (L^T x = y): y in X2, x goes to X.  Per front: X2_front -= X[rows] L[below,front] (gathered columns of X);
+//                         per outer block, last to first: X2_O -= X_later L[later,O];  X_O = X2_O Wf.
+// Two dependent launches per 512 pivot columns instead of two per 64; single-block fronts use their 64 x 64 inverse the
+// same way.  Works for both the matrix-vector kernel (k <= 4) and the tensor-core tiles.
+enum { SP_X2 = 1 };
+static inline void fsolve_node_steps_outer(LevelBuilder &B, const SNode &x, int k, int kp, std::vector<Step> &q)
+{
+    const int64_t xs = (int64_t)x.first * kp;
+    const int no = x.winv >= 0 ? n_outer(x) : 1;
+    for (int o = 0; o < no; o++) {
+        int c0, w, ldw; int64_t wf;
+        if (x.winv >= 0) { const OuterBlk ob = outer_block(x, o); c0 = ob.c0; w = ob.w; ldw = ob.ldw; wf = ob.wf; }
+        else { c0 = 0; w = x.nc; ldw = NB; wf = x.dinv; }
+        const int cE = c0 + w;
+        // X2_O += X_O Wf^T      (B(j,kk) = Wf(j,kk): tile dimension contiguous)
+        B.add_solve(q, B.task(SP_X, xs + (int64_t)c0 * kp, kp, SP_DINV, wf, ldw,
+                              SP_X2, xs + (int64_t)c0 * kp, kp, k, w, w, 0), false);
+        if (cE < x.nc)      // X_later -= X2_O L[later,O]^T
+            B.add_solve(q, B.task(SP_X2, xs + (int64_t)c0 * kp, kp, SP_L, x.panel + cE + (int64_t)c0 * x.ld, x.ld,
+                                  SP_X, xs + (int64_t)cE * kp, kp, k, x.nc - cE, w, GF_NEG), false);
+    }
+    if (x.nr > 0) {
+        GemmTask t = B.task(SP_X2, xs, kp, SP_L, x.panel + x.ncp, x.ld, SP_X, 0, kp, k, x.nr, x.nc,
+                            GF_NEG | GF_SCATTER_C | GF_ATOMIC);
+        t.cidx = (int)x.rows;
+        B.add_solve(q, t, false);
+    }
+}
+
+static inline void bsolve_node_steps_outer(LevelBuilder &B, const SNode &x, int k, int kp, std::vector<Step> &q)
+{
+    const int64_t xs = (int64_t)x.first * kp;
+    if (x.nr > 0) {
+        // X2_front -= X[rows below] L[below,front]   (columns of X gathered through the row list)
+        GemmTask t = B.task(SP_X, 0, kp, SP_L, x.panel + x.ncp, x.ld, SP_X2, xs, kp, k, x.nc, x.nr,
+                            GF_NEG | GF_GATHER_A);
+        t.aidx = (int)x.rows;
+        B.add_solve(q, t, true);
+    }
+    const int no = x.winv >= 0 ? n_outer(x) : 1;
+    for (int o = no - 1; o >= 0; o--) {
+        int c0, w, ldw; int64_t wf;
+        if (x.winv >= 0) { const OuterBlk ob = outer_block(x, o); c0 = ob.c0; w = ob.w; ldw = ob.ldw; wf = ob.wf; }
+        else { c0 = 0; w = x.nc; ldw = NB; wf = x.dinv; }
+        const int cE = c0 + w;
+        if (cE < x.nc)      // X2_O -= X_later L[later,O]     (B(j,kk) = L(cE+kk, c0+j): K contiguous)
+            B.add_solve(q, B.task(SP_X, xs + (int64_t)cE * kp, kp, SP_L, x.panel + cE + (int64_t)c0 * x.ld, x.ld,
+                                  SP_X2, xs + (int64_t)c0 * kp, kp, k, w, x.nc - cE, GF_NEG), true);
+        // X_O = X2_O Wf       (B(j,kk) = Wf(kk,j): K contiguous)
+        B.add_solve(q, B.task(SP_X2, xs + (int64_t)c0 * kp, kp, SP_DINV, wf, ldw,
+                              SP_X, xs + (int64_t)c0 * kp, kp, k, w, w, GF_BETA0), true);
+    }
+}
+
 // Hoisted, once per level: Wf of every outer block of the given fronts and the seeds Z[O,O] = Wf^T Wf, in seven grouped
 // launches.  `yoff[i]` = scratch of front i in the Y space.
 static inline void winv_level_launches(Program &P, const std::vector<const SNode *> &nodes, const std::vector<int64_t> &yoff, int sp_z,
-                                       bool from_factor = false)
+                                       bool from_factor = false, bool seeds = true)
 {
     if (!from_factor) {
         Launch L;
@@ -789,7 +856,7 @@ static inline void winv_level_launches(Program &P, const std::vector<const SNode
     LevelBuilder B(P);
     for (size_t fi = 0; fi < nodes.size(); fi++) {
         std::vector<Step> q;
-        winv_doubling_steps(B, *nodes[fi], 0, n_outer(*nodes[fi]), yoff[fi], sp_z, q, !from_factor, true);
+        winv_doubling_steps(B, *nodes[fi], 0, n_outer(*nodes[fi]), yoff[fi], sp_z, q, !from_factor, seeds);
         B.seq.push_back(std::move(q));
     }
     B.flush();

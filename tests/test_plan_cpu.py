@@ -140,15 +140,20 @@ def test_emulated_large_fronts(shape):
     assert np.abs(full[mask] - Zd[mask]).max() < 1e-10 * np.abs(Zd).max()
 
 
-@pytest.mark.parametrize("blocks,kchunk2,diag", [("2", "0", "1"), ("3", "96", "1"), ("1", "2048", "1"), ("2", "0", "0"), ("3", "96", "0")])
-def test_emulated_selinv_outer_blocks(monkeypatch, blocks, kchunk2, diag):
+@pytest.mark.parametrize("blocks,kchunk2,diag,solve_outer", [("2", "0", "1", "1"), ("3", "96", "1", "1"), ("1", "2048", "1", "0"),
+                                                             ("2", "0", "0", "1"), ("3", "96", "0", "1"), ("2", "0", "0", "0"),
+                                                             ("3", "96", "0", "0")])
+def test_emulated_selinv_outer_blocks(monkeypatch, blocks, kchunk2, diag, solve_outer):
     """Two-level Takahashi recursion with several outer blocks per front (normally 512 columns wide): outer-block
     inverses by recursive doubling (ragged last block, non-power-of-two block counts), unsplit and K-chunked products;
     and the same mesh through the 64-column recursion (SPDE_SELINV_OUTER=0) gives the same selected inverse.  diag = 1: the
     factorisation itself works on outer blocks (diagonal-first panels, one out-of-place TRSM with the outer-block inverse
     per 512 columns, block copies) and leaves the inverses for the recursion; diag = 0: blocked left-looking panels, the
-    recursion builds the inverses (what the streamed schedules do)."""
+    recursion builds the inverses (what the streamed schedules do) -- unless solve_outer = 1 (the default): then the factor
+    schedule ends with an epilogue that builds the inverses of the whole tree, and the triangular solves work on outer
+    blocks with two right-hand-side buffers."""
     monkeypatch.setenv("SPDE_FACTOR_DIAG", diag)
+    monkeypatch.setenv("SPDE_SOLVE_OUTER_BLOCKS", solve_outer)
     monkeypatch.setenv("SPDE_SELINV_OUTER_BLOCKS", blocks)
     monkeypatch.setenv("SPDE_SELINV_KCHUNK2", kchunk2)
     M, N, T, bc = 24, 22, 9, 3
@@ -162,14 +167,26 @@ def test_emulated_selinv_outer_blocks(monkeypatch, blocks, kchunk2, diag):
     A = sparse.csc_matrix(A + sparse.diags(np.abs(A).sum(axis=1).A1 + 1.0))
     em = pe.Emulator(plan)
     assert em.factorize(pat.from_sparse(A)) == 0
-    prog = pe.Program(plan, 0 if diag == "1" else 3)
+    assert em.solve_outer == (solve_outer == "1")
+    in_factor = diag == "1" or solve_outer == "1"
+    prog = pe.Program(plan, 0 if in_factor else 3)
     assert (prog.wtw["pad"] == 1).any()                    # copy-mode tasks: the outer-block inverses are built here
-    assert (len(prog.bcopy) > 0) == (diag == "1")
+    assert (len(pe.Program(plan, 0).bcopy) > 0) == (diag == "1")
     Ad = A.toarray()
     sign, ld0 = np.linalg.slogdet(Ad)
     assert abs(em.logdet() - ld0) < 1e-11 * abs(ld0)
     Bm = rng.normal(size=(n, 2))
     assert np.abs(Ad @ em.solve(Bm, mode=15) - Bm).max() < 1e-10 * np.abs(Bm).max()
+    perm = plan.perm.astype(np.int64)
+    Lref = np.linalg.cholesky(Ad[np.ix_(perm, perm)])
+    for k in (1, 2, 5):          # forward only / backward only, matrix-vector and tile kernels, odd column counts
+        Bk = rng.normal(size=(n, k))
+        Y = em.solve(Bk, mode=5)         # L^-1 P b
+        assert np.abs(Y - np.linalg.solve(Lref, Bk[perm])).max() < 1e-10 * np.abs(Y).max()
+        Zs = em.solve(Bk, mode=10)       # P^T L^-T z
+        ref = np.empty_like(Bk)
+        ref[perm] = np.linalg.solve(Lref.T, Bk)
+        assert np.abs(Zs - ref).max() < 1e-10 * np.abs(ref).max()
     Zq = em.selinv()
     Zd = np.linalg.inv(A.toarray())
     full = pat.to_csc(Zq).toarray()
