@@ -476,10 +476,12 @@ static cudaError_t launch_gemm(const Launch &L, const Program &P, const GemmSpac
         if (cfg == 9) return launch_gemm_variant<64, 64, 2, 2, false, false, 32, 2>(L, P, sp, st);    // k-tile 32, 2 stages
         if (cfg == 10) return launch_gemm_variant<64, 64, 2, 2, false, false, 32, 3>(L, P, sp, st);   // k-tile 32, 3 stages
         if (cfg == 11) return launch_gemm_variant<64, 64, 2, 2, false, false, 16, 4>(L, P, sp, st);   // 4 stages
-        if (cfg == 12) return launch_gemm_variant<64, 128, 2, 4, false, false, 32, 2>(L, P, sp, st);  // 64x128, k-tile 32
-        if (cfg == 13) return launch_gemm_variant<64, 64, 2, 2, false, false, 8, 4>(L, P, sp, st);    // k-tile 8, 4 stages
-        if (cfg == 14) return launch_gemm_variant<64, 64, 1, 4, false, false, 16, 3>(L, P, sp, st);   // warp tiles 64x16
-        if (cfg == 15) return launch_gemm_variant<64, 64, 4, 1, false, false, 16, 3>(L, P, sp, st);   // warp tiles 16x64
+        // deep pipelines for launches with about one CTA per SM (the skinny products of the panel chain): a CTA alone on
+        // its SM exposes one memory latency per k-tile unless several k-tiles are in flight
+        if (cfg == 12) return launch_gemm_variant<64, 64, 2, 2, false, false, 32, 4>(L, P, sp, st);   // k-tile 32, 4 stages
+        if (cfg == 13) return launch_gemm_variant<64, 64, 2, 2, false, false, 64, 2>(L, P, sp, st);   // k-tile 64, 2 stages
+        if (cfg == 14) return launch_gemm_variant<64, 64, 2, 2, false, false, 64, 3>(L, P, sp, st);   // k-tile 64, 3 stages
+        if (cfg == 15) return launch_gemm_variant<64, 64, 2, 2, false, false, 32, 6>(L, P, sp, st);   // k-tile 32, 6 stages
     }
     return cudaErrorInvalidValue;
 }

@@ -175,10 +175,47 @@ struct LevelBuilder {
         std::vector<int> order;
         for (const Step *st : steps)
             for (int g = st->g0; g < st->g0 + st->gn; g++) order.push_back(g);
-        std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return pool[x].K > pool[y].K; });
+        // Under-filled launches: a 64x64 tile is bound by the FP64 tensor pipe of the ONE SM it runs on (1.1 us per 32-deep
+        // k-tile, tools/deep_sweep.py), so a launch with fewer tiles than SMs takes as long as its longest K however few
+        // tiles it has.  Accumulating tasks of such a launch are cut along K into chunks that accumulate atomically, until
+        // the launch has about one tile per SM.
+        std::vector<GemmTask> cut;
+        {
+            static const int splitk = env_int("SPDE_SMALL_SPLITK", 1, 0);
+            long long nt = 0;
+            int kmax = 0;
+            bool ok = splitk != 0 && cfg == 2;
+            for (int g : order) {
+                nt += count_tiles(pool[g], cfg);
+                kmax = std::max(kmax, pool[g].K);
+                if (pool[g].flags & GF_BETA0) ok = false;
+            }
+            int nsplit = (ok && nt > 0 && nt * 2 <= kSMs) ? (int)std::min<long long>(kSMs / nt, kmax / 64) : 1;
+            if (nsplit > 1) {
+                const int ak = (key >> 1) & 1, bk = key & 1;
+                for (int g : order) {
+                    const GemmTask &t = pool[g];
+                    int clen = (t.K + nsplit - 1) / nsplit;
+                    clen = std::max(64, (clen + 31) / 32 * 32);
+                    for (int k0 = 0; k0 < t.K; k0 += clen) {
+                        GemmTask c = t;
+                        c.K = std::min(clen, t.K - k0);
+                        c.flags |= GF_ATOMIC;
+                        if (t.flags & GF_GATHER_A) c.aidx += k0;
+                        else c.a += ak ? (long long)k0 : (long long)k0 * t.lda;
+                        c.b += bk ? (long long)k0 : (long long)k0 * t.ldb;
+                        cut.push_back(c);
+                    }
+                }
+                order.clear();
+                for (size_t i = 0; i < cut.size(); i++) order.push_back((int)i);
+            }
+        }
+        const std::vector<GemmTask> &src = cut.empty() ? pool : cut;
+        std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return src[x].K > src[y].K; });
         for (int g : order) {
             {
-                const GemmTask &t = pool[g];
+                const GemmTask &t = src[g];
                 const int id = (int)(prog.gemm.size() - L.task0);
                 prog.gemm.push_back(t);
                 const int tm = (t.M + BM - 1) / BM, tn = (t.N + BN - 1) / BN;
