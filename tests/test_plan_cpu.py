@@ -140,9 +140,8 @@ def test_emulated_large_fronts(shape):
     assert np.abs(full[mask] - Zd[mask]).max() < 1e-10 * np.abs(Zd).max()
 
 
-@pytest.mark.parametrize("blocks,kchunk2,diag,solve_outer", [("2", "0", "1", "1"), ("3", "96", "1", "1"), ("1", "2048", "1", "0"),
-                                                             ("2", "0", "0", "1"), ("3", "96", "0", "1"), ("2", "0", "0", "0"),
-                                                             ("3", "96", "0", "0")])
+@pytest.mark.parametrize("blocks,kchunk2,diag,solve_outer", [("2", "0", "1", "1"), ("1", "2048", "1", "0"), ("2", "0", "0", "1"),
+                                                             ("3", "96", "0", "1"), ("3", "96", "0", "0")])
 def test_emulated_selinv_outer_blocks(monkeypatch, blocks, kchunk2, diag, solve_outer):
     """Two-level Takahashi recursion with several outer blocks per front (normally 512 columns wide): outer-block
     inverses by recursive doubling (ragged last block, non-power-of-two block counts), unsplit and K-chunked products;
@@ -179,7 +178,7 @@ def test_emulated_selinv_outer_blocks(monkeypatch, blocks, kchunk2, diag, solve_
     assert np.abs(Ad @ em.solve(Bm, mode=15) - Bm).max() < 1e-10 * np.abs(Bm).max()
     perm = plan.perm.astype(np.int64)
     Lref = np.linalg.cholesky(Ad[np.ix_(perm, perm)])
-    for k in (1, 2, 5):          # forward only / backward only, matrix-vector and tile kernels, odd column counts
+    for k in ((1, 5) if kchunk2 == "0" else (2,)):      # forward only / backward only, matrix-vector and tile kernels, odd column counts
         Bk = rng.normal(size=(n, k))
         Y = em.solve(Bk, mode=5)         # L^-1 P b
         assert np.abs(Y - np.linalg.solve(Lref, Bk[perm])).max() < 1e-10 * np.abs(Y).max()
