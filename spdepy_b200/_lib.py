@@ -177,7 +177,7 @@ class PlanHandle:
                 "factor_bytes": self.info(4), "arena_bytes": self.info(5), "levels": self.info(6),
                 "max_front": self.info(7), "max_cols": self.info(13), "launches": self.info(8),
                 "gemm_tasks": self.info(11), "tiles": self.info(12), "zarena_bytes": self.info(10),
-                "sched_flops": self.info_d(14)}
+                "sched_flops": self.info_d(14), "dinv_bytes": self.info(15), "ybuf_bytes": self.info(16)}
 
     def __del__(self):
         try:

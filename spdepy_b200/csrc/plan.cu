@@ -902,6 +902,8 @@ extern "C" int64_t spde_plan_info(const spde_plan *pp, int what)
     case 11: return (int64_t)p->factor.gemm.size();
     case 12: return (int64_t)p->factor.tiles.size();
     case 13: { int m = 0; for (auto &s : p->sn) m = std::max(m, s.nc); return m; }
+    case 15: return p->dinv_size * 8;      // inverse diagonal blocks + outer-block inverses
+    case 16: return p->ybuf_size * 8;      // scratch of the outer-block products
     }
     return -1;
 }

@@ -344,7 +344,7 @@ class Engine:
     def incore_bytes(self) -> int:
         """Device bytes of one factor store with its update-matrix arenas and inverse fronts (the in-core path)."""
         st = self.plan.stats()
-        return st["factor_bytes"] + st["arena_bytes"] + st["zarena_bytes"]
+        return st["factor_bytes"] + st["arena_bytes"] + st["zarena_bytes"] + st["dinv_bytes"] + st["ybuf_bytes"]
 
     def use_streamed(self, stores: int = 1) -> bool:
         """``stores``: factor stores the caller needs resident at once (2 for the Hutchinson mode, which keeps the 3-D
