@@ -35,6 +35,24 @@ def _stream():
 COUNTERS = {"h2d": 0, "d2h": 0, "calls": 0}
 
 
+class nvtx_range:
+    """NVTX range around a phase of the hot path (assembly, factorisation, solves, Takahashi, gradient contraction) when
+    ``SPDE_NVTX=1``: the ranges show up in any CUDA timeline tool; a no-op otherwise."""
+    enabled = os.environ.get("SPDE_NVTX", "0") not in ("0", "")
+
+    def __init__(self, name: str):
+        self.name = name
+
+    def __enter__(self):
+        if nvtx_range.enabled:
+            torch.cuda.nvtx.range_push(self.name)
+        return self
+
+    def __exit__(self, *a):
+        if nvtx_range.enabled:
+            torch.cuda.nvtx.range_pop()
+
+
 def to_dev(a, dtype=F64) -> torch.Tensor:
     if isinstance(a, torch.Tensor):
         if not a.is_cuda:

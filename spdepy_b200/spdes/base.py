@@ -21,7 +21,7 @@ import numpy as np
 import torch
 from scipy import sparse
 
-from ..engine import COUNTERS, F64, Engine, Lazy, ScalarPool, to_dev, to_host
+from ..engine import COUNTERS, F64, Engine, Lazy, ScalarPool, nvtx_range, to_dev, to_host
 
 
 class SPDE2D:
@@ -648,7 +648,8 @@ class SPDE2D:
         if data is None:
             data = to_dev(self.data.reshape(nobs, r))
         tau = float(np.exp(par[-1]))
-        st = self._assemble(par)
+        with nvtx_range("spde.assemble (K2/K3)"):
+            st = self._assemble(par)
         self._state = st
         Q = st["Q"]
         # space-time prior: its determinant (and hence every prior trace of the gradient) factorises over
@@ -661,9 +662,10 @@ class SPDE2D:
                                           "a space-time model with exact_grad=True or grad=False")
             return self._logLike_streamed(par, st, data, obs, cnt, tau, grad)
         if collapsed:
-            eng.factorize_async(1, Q, cnt, tau)
-            prior = self._prior_collapsed(st, want_grad=grad)
-            eng.factor_wait(1)
+            with nvtx_range("spde.factorize Q_c (K4/K5) + collapsed prior"):
+                eng.factorize_async(1, Q, cnt, tau)
+                prior = self._prior_collapsed(st, want_grad=grad)
+                eng.factor_wait(1)
             ldQ = prior["logdet"]
         else:
             prior = None
@@ -681,10 +683,12 @@ class SPDE2D:
         ldQc = self._logdet(eng, 1)
         overlap = grad and exact_grad and collapsed
         if overlap:
-            eng.selinv_start(1)     # the Takahashi pass runs beside the (latency-bound) solve and reductions below
-        mu_c = eng.solve(1, eng.scatter_obs(data, obs, tau))          # Q_c^-1 S^T data tau
-        quad = self._dot(mu_c, eng.q_apply(Q, mu_c))
-        resid = self._resid(data, mu_c, obs)
+            with nvtx_range("spde.selinv start (K10)"):
+                eng.selinv_start(1)     # the Takahashi pass runs beside the (latency-bound) solve and reductions below
+        with nvtx_range("spde.solve mu_c + reductions (K7/K8)"):
+            mu_c = eng.solve(1, eng.scatter_obs(data, obs, tau))          # Q_c^-1 S^T data tau
+            quad = self._dot(mu_c, eng.q_apply(Q, mu_c))
+            resid = self._resid(data, mu_c, obs)
         like = 1 / 2 * ldQ * r + nobs * r * np.log(tau) / 2 - 1 / 2 * ldQc * r - 1 / 2 * quad - tau / 2 * resid
         self.last = {"mu_c": mu_c, "logdetQ": ldQ, "logdetQc": ldQc, "quad": quad, "resid": resid}
         if not grad:
@@ -712,10 +716,11 @@ class SPDE2D:
             W = eng.sddmm(TrQ, Vp, a)
             W = eng.sddmm(TrQc, Vp, -a, W)
             tr_tau = self._wdot(TrQc, Vp, cnt) * tau / nh1
-        W = eng.sddmm(mu_c, mu_c, -0.5, W)
-        gi = self._grad_from_weights(st, W, prior)
-        g_last = nobs * r / 2 - 1 / 2 * tr_tau * r - tau / 2 * resid
-        return self._finish(like, nobs * r, gi, g_last, par.size)
+        with nvtx_range("spde.gradient contraction (K9/K11)"):
+            W = eng.sddmm(mu_c, mu_c, -0.5, W)
+            gi = self._grad_from_weights(st, W, prior)
+            g_last = nobs * r / 2 - 1 / 2 * tr_tau * r - tau / 2 * resid
+            return self._finish(like, nobs * r, gi, g_last, par.size)
 
 
     def _logLike_streamed(self, par, st, data, obs, cnt, tau, grad):
