@@ -2,6 +2,7 @@
 // extend-add, gathers, reductions), the program executor and the C ABI for plan / factor / solve
 // / selected inverse.
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 
@@ -539,6 +540,12 @@ static int issue_program(Plan &p, Program &P, int which, cudaStream_t st, double
     if (rc) return rc;
     ExecCtx ctx;
     ctx.sp = spaces_of(p, which, &P != &p.factor && &P != &p.selinv);
+    if (getenv("SPDE_DEBUG_PTRS")) {
+        fprintf(stderr, "# spaces (n=%d, which=%d, prog=%s):", p.sym.n, which, &P == &p.factor ? "factor" : (&P == &p.selinv ? "selinv" : "solve"));
+        for (int i = 0; i < 8; i++) fprintf(stderr, " %d:%p", i, (void *)ctx.sp.base[i]);
+        fprintf(stderr, " sizes L=%lld dinv=%lld ybuf=%lld z0=%lld z1=%lld\n", (long long)p.l_size, (long long)p.dinv_size, (long long)p.ybuf_size,
+                (long long)p.zarena_size[0], (long long)p.zarena_size[1]);
+    }
     ctx.L = p.d_L[which]; ctx.dinv = p.d_dinv[which]; ctx.status = p.d_status + which;
     ctx.zent = p.d_zentries; ctx.Zq = d_Zq; ctx.which = which; ctx.lanes = true;
     return issue_program_ex(p, P, ctx, st);
@@ -830,6 +837,9 @@ static int ensure_device(Plan &p, int which)
         SPDE_CUDA_CHECK(cudaMemset(p.d_dinv[which], 0, std::max<int64_t>(p.dinv_size, 2) * sizeof(double)));
         // scratch of the outer-block products (factorisation: doubling rounds and the out-of-place TRSM; Takahashi: Yt)
         SPDE_CUDA_CHECK(cudaMalloc((void **)&p.d_ybuf[which], std::max<int64_t>(p.ybuf_size, 2) * sizeof(double)));
+        // (zeroed once: a 16-byte cp.async with src-size 8 on the last row of an odd-height tile names the pad row behind it,
+        // which no kernel writes -- it is zero-filled in shared memory, not read, but initcheck would flag the address)
+        SPDE_CUDA_CHECK(cudaMemset(p.d_ybuf[which], 0, std::max<int64_t>(p.ybuf_size, 2) * sizeof(double)));
     }
     return SPDE_OK;
 }
