@@ -27,6 +27,8 @@ enum : int {
     GF_GATHER_A = 1 << 13,  // column kk of A is column idx[aidx+kk] of the A space
     GF_SCATTER_C = 1 << 14, // column j of C is column idx[cidx+j] of the C space
     GF_UPPER_MIRROR = 1 << 15, // also write the transposed block at c2 (keeps selected-inverse fronts symmetric)
+    GF_ZDEST = 1 << 16,     // schedule hint (ignored by the kernels): C holds zeros before this launch, so a BETA0 task may be
+                            // cut along K into chunks that accumulate atomically
 };
 
 struct GemmTask {

@@ -211,6 +211,49 @@ struct LevelBuilder {
                 for (size_t i = 0; i < cut.size(); i++) order.push_back((int)i);
             }
         }
+        // Wave balance: a launch of T equal-length tiles on S resident slots takes ceil(T/S) tile times; with T a few
+        // times S the last, partly filled wave is a sizeable fraction of the launch.  Cutting every task along K into s
+        // chunks (atomic accumulation) makes s T shorter tiles: ceil(s T / S) / s tile times.  Applied when it saves more than
+        // the atomics cost (~3 % per extra chunk), to launches whose tasks all accumulate (or write a zeroed block, GF_ZDEST).
+        if (cut.empty()) {
+            static const int wavebal = env_int("SPDE_WAVE_BALANCE", 1, 0);
+            const long long S = (cfg == CFG_WS ? 2 : 4) * (long long)kSMs;
+            long long T = 0;
+            int kmin = 1 << 30;
+            bool ok = wavebal != 0 && (cfg == CFG_WS || cfg == 2);
+            for (int g : order) {
+                T += count_tiles(pool[g], cfg);
+                kmin = std::min(kmin, pool[g].K);
+                if ((pool[g].flags & GF_BETA0) && !(pool[g].flags & GF_ZDEST)) ok = false;
+            }
+            if (ok && T >= S && T < 8 * S) {
+                int best = 1;
+                double bc = (double)((T + S - 1) / S);
+                for (int sp = 2; sp <= 4 && kmin / sp >= 128; sp++) {
+                    const double c = (double)((T * sp + S - 1) / S) / sp * (1.0 + 0.03 * (sp - 1));
+                    if (c < bc * 0.97) { bc = c; best = sp; }
+                }
+                if (best > 1) {
+                    const int ak = (key >> 1) & 1, bk = key & 1;
+                    for (int g : order) {
+                        const GemmTask &t = pool[g];
+                        int clen = (t.K + best - 1) / best;
+                        clen = (clen + 31) / 32 * 32;
+                        for (int k0 = 0; k0 < t.K; k0 += clen) {
+                            GemmTask c = t;
+                            c.K = std::min(clen, t.K - k0);
+                            c.flags = (c.flags & ~GF_BETA0) | GF_ATOMIC;
+                            if (t.flags & GF_GATHER_A) c.aidx += k0;
+                            else c.a += ak ? (long long)k0 : (long long)k0 * t.lda;
+                            c.b += bk ? (long long)k0 : (long long)k0 * t.ldb;
+                            cut.push_back(c);
+                        }
+                    }
+                    order.clear();
+                    for (size_t i = 0; i < cut.size(); i++) order.push_back((int)i);
+                }
+            }
+        }
         const std::vector<GemmTask> &src = cut.empty() ? pool : cut;
         std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return src[x].K > src[y].K; });
         for (int g : order) {
@@ -618,7 +661,7 @@ static inline void selinv_node_steps(LevelBuilder &B, const SNode &x, int sp_z, 
         for (int k0 = 0, ci = 0; k0 < mb; k0 += clen, ci++) {
             GemmTask t = B.task(sp_z, F + r0 + (int64_t)(r0 + k0) * x.ld, x.ld, SP_Y, Y + (int64_t)k0 * NB, NB,
                                 sp_z, F + r0 + (int64_t)c0 * x.ld, x.ld, mb, b, std::min(clen, mb - k0),
-                                GF_NEG | GF_UPPER_MIRROR | (nchunk == 1 ? GF_BETA0 : GF_ATOMIC));
+                                GF_NEG | GF_UPPER_MIRROR | (nchunk == 1 ? (GF_BETA0 | GF_ZDEST) : GF_ATOMIC));
             t.c2 = F + c0 + (int64_t)r0 * x.ld;
             if (ci == 0) B.add_gemm(q, t, false, false);
             else B.join_gemm(q, t);
@@ -946,7 +989,7 @@ static inline void selinv_node_steps_outer(LevelBuilder &B, const SNode &x, int 
         for (int k0 = 0, ci = 0; k0 < mb; k0 += clen, ci++) {
             GemmTask t = B.task(sp_z, F + r0 + (int64_t)(r0 + k0) * x.ld, x.ld, SP_Y, Y + (int64_t)k0 * ldY, ldY,
                                 sp_z, F + r0 + (int64_t)c0 * x.ld, x.ld, mb, w, std::min(clen, mb - k0),
-                                GF_NEG | GF_UPPER_MIRROR | (nchunk == 1 ? GF_BETA0 : GF_ATOMIC));
+                                GF_NEG | GF_UPPER_MIRROR | (nchunk == 1 ? (GF_BETA0 | GF_ZDEST) : GF_ATOMIC));
             t.c2 = F + c0 + (int64_t)r0 * x.ld;
             if (ci == 0) B.add_gemm(q, t, false, false);
             else B.join_gemm(q, t);
