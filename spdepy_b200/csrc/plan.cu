@@ -540,12 +540,6 @@ static int issue_program(Plan &p, Program &P, int which, cudaStream_t st, double
     if (rc) return rc;
     ExecCtx ctx;
     ctx.sp = spaces_of(p, which, &P != &p.factor && &P != &p.selinv);
-    if (getenv("SPDE_DEBUG_PTRS")) {
-        fprintf(stderr, "# spaces (n=%d, which=%d, prog=%s):", p.sym.n, which, &P == &p.factor ? "factor" : (&P == &p.selinv ? "selinv" : "solve"));
-        for (int i = 0; i < 8; i++) fprintf(stderr, " %d:%p", i, (void *)ctx.sp.base[i]);
-        fprintf(stderr, " sizes L=%lld dinv=%lld ybuf=%lld z0=%lld z1=%lld\n", (long long)p.l_size, (long long)p.dinv_size, (long long)p.ybuf_size,
-                (long long)p.zarena_size[0], (long long)p.zarena_size[1]);
-    }
     ctx.L = p.d_L[which]; ctx.dinv = p.d_dinv[which]; ctx.status = p.d_status + which;
     ctx.zent = p.d_zentries; ctx.Zq = d_Zq; ctx.which = which; ctx.lanes = true;
     return issue_program_ex(p, P, ctx, st);
