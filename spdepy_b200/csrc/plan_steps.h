@@ -267,7 +267,8 @@ struct LevelBuilder {
                 // operand panel is fetched from DRAM once per group of resident tiles that share it.  Column-major order
                 // makes ~4 tile columns resident: every A row panel is shared by 4 tiles only.  Supertiles of SJ x SI
                 // (16 x 16, or all columns x 256/columns for narrow products) share A panels 16-fold and B panels 16-fold.
-                const int SJ = std::min(tn, 16), SI = std::max(1, 256 / SJ);
+                static const int sjmax = env_int("SPDE_SUPERTILE", 16, 1);      // (sweep hook: 8 / 16 / 32 columns of tiles)
+                const int SJ = std::min(tn, sjmax), SI = std::max(1, 256 / SJ);
                 for (int tj0 = 0; tj0 < tn; tj0 += SJ)
                     for (int ti0 = 0; ti0 < tm; ti0 += SI)
                         for (int tj = tj0; tj < std::min(tj0 + SJ, tn); tj++)
