@@ -174,6 +174,112 @@ __global__ void k_sddmm(Geo g, const double *__restrict__ X, const double *__res
     }
 }
 
+// Many probe columns (the Hutchinson estimator, nh1 = 100): patch-tiled version.  One CTA owns an 8 x 8 patch of cells of one
+// time slice; the probe rows of the patch (X) and of its halo (Y: radius 2 in the slice, radius 1 or 2 in the slices before
+// and after, as the pattern says) are staged in shared memory 32 columns at a time, and every thread accumulates a
+// handful of (node, slot) dot products from there.  The warp-per-node kernel above fetches each Y row once per node that
+// touches it (43 times, from L2); here it is fetched once per patch.  Same products, summed over the columns in order.
+constexpr int SD_PW = 8, SD_PH = 8, SD_KC = 32, SD_THREADS = 256, SD_MAXPAIRS = 19;     // 75 slots x 64 nodes / 256 threads
+__global__ void __launch_bounds__(SD_THREADS) k_sddmm_tiled(Geo g, const double *__restrict__ X, const double *__restrict__ Y, int k,
+                                                            double alpha, int accumulate, double *__restrict__ W)
+{
+    extern __shared__ __align__(16) double sd_smem[];
+    const int ns = g.nslots(), Ns = g.M * g.N;
+    const long long n = (long long)Ns * g.T;
+    const int rad_t = (g.T == 1) ? 0 : (g.pat == 1 ? 2 : 1);       // halo radius in the neighbouring slices (0: none)
+    const int w0 = SD_PW + 4, h0 = SD_PH + 4, w1 = SD_PW + 2 * rad_t, h1 = SD_PH + 2 * rad_t;
+    const int nh0 = w0 * h0, nh1 = rad_t ? w1 * h1 : 0;
+    const int nhalo = nh0 + 2 * nh1;                               // [slice t | slice t-1 | slice t+1]
+    double *Xs = sd_smem;                                          // [64][KC+1]
+    double *Ys = Xs + SD_PW * SD_PH * (SD_KC + 1);                 // [nhalo][KC+1]
+    int *hnode = reinterpret_cast<int *>(Ys + (size_t)nhalo * (SD_KC + 1));
+    const int px = (g.M + SD_PW - 1) / SD_PW, py = (g.N + SD_PH - 1) / SD_PH;
+    const int bid = blockIdx.x;
+    const int t = bid / (px * py), pj = (bid / px) % py, pi = bid % px;
+    const int i0 = pi * SD_PW, j0 = pj * SD_PH;
+    const int tid = threadIdx.x;
+    // global node of every halo cell (-1: outside the mesh / the time range)
+    for (int h = tid; h < nhalo; h += SD_THREADS) {
+        int dt, hh = h, ww, rad;
+        if (h < nh0) { dt = 0; ww = w0; rad = 2; }
+        else if (h < nh0 + nh1) { dt = -1; hh = h - nh0; ww = w1; rad = rad_t; }
+        else { dt = 1; hh = h - nh0 - nh1; ww = w1; rad = rad_t; }
+        const int hi = hh % ww, hj = hh / ww;
+        const int tt = t + dt;
+        int node = -1;
+        if (tt >= 0 && tt < g.T) {
+            // (cells of the patch row / column beyond the mesh edge have no node; wrapped neighbours under bc = 2)
+            int ii = i0 + hi - rad, jj = j0 + hj - rad;
+            if (g.bc == 2) {
+                ii = ii < 0 ? ii + g.M : (ii >= g.M ? ii - g.M : ii);
+                jj = jj < 0 ? jj + g.N : (jj >= g.N ? jj - g.N : jj);
+            }
+            if (ii >= 0 && ii < g.M && jj >= 0 && jj < g.N) node = tt * Ns + jj * g.M + ii;
+        }
+        hnode[h] = node;
+    }
+    // pairs (slot q, patch cell c) of this thread: e = tid + 256 m, c = e % 64 (fastest: coalesced rows of W), q = e / 64
+    const int npairs = ns * SD_PW * SD_PH;
+    int prow[SD_MAXPAIRS];
+    double acc[SD_MAXPAIRS];
+#pragma unroll
+    for (int m = 0; m < SD_MAXPAIRS; m++) {
+        acc[m] = 0.0;
+        prow[m] = -1;
+        const int e = tid + SD_THREADS * m;
+        if (e < npairs) {
+            const int c = e % (SD_PW * SD_PH), q = e / (SD_PW * SD_PH);
+            const int il = c % SD_PW, jl = c / SD_PW;
+            if (i0 + il < g.M && j0 + jl < g.N) {
+                int dt, dj, di;
+                g.slot_offset(q, dt, dj, di);
+                // the neighbour the pattern names must exist (same rule as slot_nbr), and it is a halo cell by construction
+                const int node = t * Ns + (j0 + jl) * g.M + (i0 + il);
+                if (g.slot_nbr(node, q) >= 0) {
+                    if (dt == 0) prow[m] = (jl + dj + 2) * w0 + (il + di + 2);
+                    else prow[m] = nh0 + (dt > 0 ? nh1 : 0) + (jl + dj + rad_t) * w1 + (il + di + rad_t);
+                }
+            }
+        }
+    }
+    for (int k0 = 0; k0 < k; k0 += SD_KC) {
+        const int kc = min(SD_KC, k - k0);
+        __syncthreads();                      // hnode ready / previous chunk consumed
+        for (int e = tid; e < SD_PW * SD_PH * SD_KC; e += SD_THREADS) {
+            const int c = e / SD_KC, p = e % SD_KC;
+            const int il = c % SD_PW, jl = c / SD_PW;
+            double v = 0.0;
+            if (p < kc && i0 + il < g.M && j0 + jl < g.N) v = X[((long long)t * Ns + (j0 + jl) * g.M + (i0 + il)) * k + k0 + p];
+            Xs[c * (SD_KC + 1) + p] = v;
+        }
+        for (int e = tid; e < nhalo * SD_KC; e += SD_THREADS) {
+            const int h = e / SD_KC, p = e % SD_KC;
+            const int node = hnode[h];
+            Ys[h * (SD_KC + 1) + p] = (node >= 0 && p < kc) ? Y[(long long)node * k + k0 + p] : 0.0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int m = 0; m < SD_MAXPAIRS; m++) {
+            if (prow[m] < 0) continue;
+            const int c = (tid + SD_THREADS * m) % (SD_PW * SD_PH);
+            const double *xr = Xs + c * (SD_KC + 1), *yr = Ys + prow[m] * (SD_KC + 1);
+            double s = acc[m];
+#pragma unroll 8
+            for (int p = 0; p < SD_KC; p++) s += xr[p] * yr[p];
+            acc[m] = s;
+        }
+    }
+#pragma unroll
+    for (int m = 0; m < SD_MAXPAIRS; m++) {
+        if (prow[m] < 0) continue;
+        const int e = tid + SD_THREADS * m;
+        const int c = e % (SD_PW * SD_PH), q = e / (SD_PW * SD_PH);
+        const long long node = (long long)t * Ns + (j0 + c / SD_PW) * g.M + (i0 + c % SD_PW);
+        const long long o = (long long)q * n + node;
+        W[o] = accumulate ? W[o] + alpha * acc[m] : alpha * acc[m];
+    }
+}
+
 // single-column case (the -1/2 mu mu^T term of every gradient): one thread per node, slot loop unrolled by the
 // compiler, every slot one coalesced read-modify-write stream
 __global__ void k_sddmm1(Geo g, const double *__restrict__ X, const double *__restrict__ Y, double alpha,
@@ -392,6 +498,21 @@ extern "C" int spde_sddmm(int M, int N, int T, int bc, const double *d_X, const 
     const long long n = (long long)M * N * T;
     if (k == 1) {
         k_sddmm1<<<(int)std::min<long long>((n + 255) / 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(g, d_X, d_Y, alpha, accumulate, d_W);
+    } else if (k >= 16 && !getenv("SPDE_SDDMM_WARP")) {
+        // patch-tiled kernel: shared memory = probe rows of the patch and of its halo, 32 columns at a time
+        const int rad_t = (T == 1) ? 0 : (g.pat == 1 ? 2 : 1);
+        const int nhalo = (SD_PW + 4) * (SD_PH + 4) + (rad_t ? 2 * (SD_PW + 2 * rad_t) * (SD_PH + 2 * rad_t) : 0);
+        const size_t smem = (size_t)(SD_PW * SD_PH + nhalo) * (SD_KC + 1) * sizeof(double) + (size_t)nhalo * sizeof(int);
+        static bool attr_done[64] = {false};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        dev &= 63;
+        if (!attr_done[dev]) {
+            SPDE_CUDA_CHECK(cudaFuncSetAttribute(k_sddmm_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+            attr_done[dev] = true;
+        }
+        const int px = (M + SD_PW - 1) / SD_PW, py = (N + SD_PH - 1) / SD_PH;
+        k_sddmm_tiled<<<px * py * T, SD_THREADS, smem, (cudaStream_t)stream>>>(g, d_X, d_Y, k, alpha, accumulate, d_W);
     } else {
         const long long blocks = std::min<long long>((n * 32 + 255) / 256, 148 * 16);
         k_sddmm<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(g, d_X, d_Y, k, alpha, accumulate, d_W);
