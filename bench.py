@@ -226,7 +226,7 @@ def cpu_baseline(name):
     except Exception:
         pass
     spde, spde0, ha, ani, bc, M0, N0, T0, _ = WORKLOADS[name]
-    if T0 is None:
+    if T0 is None or M0 * N0 * T0 <= 100000:      # small enough to run in full (c1: 0.03 s, c2: ~10 s)
         r = reference_eval(name)
         return {"value": 1.0 / r["seconds"], "unit": UNIT, "cores": r["cores"], "kind": "port", "scaled": False,
                 "sample": "full workload: one logLike(grad=True, nh1=100) of the oracle port, %.2f s" % r["seconds"]}
