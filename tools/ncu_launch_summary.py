@@ -20,7 +20,7 @@ with open(path, newline="") as f:
         tot += v; n += 1
 print("# ncu --metrics gpu__time_duration.sum --clock-control none --csv %s" % cmd)
 print("# per-launch times are cold-cache and serialised under ncu: compare SHARES with bench.py's roofline.gemm_share_of_scheduled_time")
-gem = sum(v[1] for k, v in agg.items() if "k_gemm_grouped" in k)
-print("# total kernels %d, total %.2f ms; k_gemm_grouped (all variants) share = %.1f%%" % (n, tot, 100 * gem / max(tot, 1e-9)))
+gem = sum(v[1] for k, v in agg.items() if "k_gemm" in k)
+print("# total kernels %d, total %.2f ms; dense tiles (k_gemm_ws + k_gemm_grouped, all variants) share = %.1f%%" % (n, tot, 100 * gem / max(tot, 1e-9)))
 for k, (c, ms) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     print("%-95s n=%6d ms=%10.3f share=%5.1f%% avg_us=%9.1f" % (k[:95], c, ms, 100 * ms / tot, 1e3 * ms / c))
