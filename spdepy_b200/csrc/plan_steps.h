@@ -280,6 +280,48 @@ struct LevelBuilder {
                 prog.flops += 2.0 * t.K * (lower ? (double)t.M * t.N - 0.5 * t.N * std::min(t.M, t.N) : (double)t.M * t.N);
             }
         }
+        // Tail split: with T tiles on S resident slots the last T mod S tiles run as a partly filled wave, a whole tile time
+        // long.  For launches of many waves (too many for the global K-split above to pay) only THOSE tiles are cut along K
+        // into S / (T mod S) chunks each (one-tile tasks that accumulate atomically), so the last wave is full and short.
+        {
+            const int tailsplit = env_int("SPDE_TAIL_SPLIT", 1, 0);
+            const int slots_env = env_int("SPDE_TAIL_SLOTS", 0, 0);      // test hook: pretend the machine has this many slots
+            const long long S = slots_env ? slots_env : (cfg == CFG_WS ? 2 : 4) * (long long)kSMs;
+            const long long T = (long long)prog.tiles.size() - L.tile0;
+            const long long R = T % S;
+            if (tailsplit && (cfg == CFG_WS || cfg == 2) && T >= 2 * S && R > 0 && 2 * R <= S) {
+                const int ak = (key >> 1) & 1, bk = key & 1;
+                const int sp = (int)std::min<long long>(S / R, 8);
+                std::vector<TileRef> tail(prog.tiles.end() - R, prog.tiles.end()), keep, split;
+                prog.tiles.resize(prog.tiles.size() - R);
+                for (const TileRef &tr : tail) {
+                    const GemmTask t = prog.gemm[L.task0 + tr.task];
+                    const int i0 = tr.ti * BM, j0 = tr.tj * BN;
+                    const bool below = !(t.flags & GF_LOWER) || i0 >= j0 + BN - 1;      // no element of the tile is masked
+                    const bool accum = !(t.flags & GF_BETA0) || (t.flags & GF_ZDEST);
+                    const int nch = std::min(sp, t.K / 128);
+                    if (!below || !accum || nch < 2) { keep.push_back(tr); continue; }
+                    int clen = (t.K + nch - 1) / nch;
+                    clen = (clen + 31) / 32 * 32;
+                    for (int k0 = 0; k0 < t.K; k0 += clen) {
+                        GemmTask c = t;
+                        c.M = std::min(BM, t.M - i0); c.N = std::min(BN, t.N - j0); c.K = std::min(clen, t.K - k0);
+                        if (t.flags & GF_GATHER_A) { c.aidx = t.aidx + k0; c.a = t.a + i0; }
+                        else c.a = t.a + (ak ? (long long)i0 * t.lda + k0 : (long long)i0 + (long long)k0 * t.lda);
+                        c.b = t.b + (bk ? (long long)j0 * t.ldb + k0 : (long long)j0 + (long long)k0 * t.ldb);
+                        if (t.flags & GF_SCATTER_C) { c.cidx = t.cidx + j0; c.c = t.c + i0; }
+                        else c.c = t.c + i0 + (long long)j0 * t.ldc;
+                        c.c2 = t.c2 + j0 + (long long)i0 * t.ldc;
+                        c.flags = (t.flags & ~(GF_BETA0 | GF_LOWER)) | GF_ATOMIC;
+                        const int id = (int)(prog.gemm.size() - L.task0);
+                        prog.gemm.push_back(c);
+                        split.push_back(TileRef{id, 0, 0, 0});
+                    }
+                }
+                prog.tiles.insert(prog.tiles.end(), keep.begin(), keep.end());
+                prog.tiles.insert(prog.tiles.end(), split.begin(), split.end());
+            }
+        }
         L.ntasks = (int)(prog.gemm.size() - L.task0);
         L.ntiles = (int)(prog.tiles.size() - L.tile0);
         if (L.ntiles > 0) prog.launches.push_back(L);

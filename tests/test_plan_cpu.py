@@ -200,6 +200,38 @@ def test_emulated_selinv_outer_blocks(monkeypatch, blocks, kchunk2, diag, solve_
     assert np.abs(Z0 - Zq).max() < 1e-11 * np.abs(Zd).max()
 
 
+def test_emulated_tail_split(monkeypatch):
+    """Tail split of many-wave launches (the tiles of the partly filled last wave become one-tile, K-chunked, atomically
+    accumulating tasks): with a pretended machine of 6 slots it triggers on small meshes, in the factorisation (lower-masked
+    updates, tiles on the diagonal are kept whole), the solves and the Takahashi products (mirror writes, zero-destination)."""
+    monkeypatch.setenv("SPDE_TAIL_SLOTS", "6")
+    M, N, T, bc = 24, 22, 9, 3
+    plan = _lib.PlanHandle(M, N, T, bc)
+    pat = Pattern(M, N, T, bc)
+    n = plan.n
+    rng = np.random.default_rng(6)
+    W = pat.to_csc(rng.normal(size=pat.nslots * n))
+    A = (W + W.T) * 0.5
+    A = sparse.csc_matrix(A + sparse.diags(np.abs(A).sum(axis=1).A1 + 1.0))
+    em = pe.Emulator(plan)
+    assert em.factorize(pat.from_sparse(A)) == 0
+    for prog in (0, 3):
+        P = pe.Program(plan, prog)
+        one_tile = sum(1 for L in P.launches if L["kind"] == pe.LK_GEMM and L["ntasks"] > 0 and
+                       ((P.gemm[L["task0"]:L["task0"] + L["ntasks"]]["flags"] & pe.GF_ATOMIC) != 0).any())
+        assert one_tile > 0
+    Ad = A.toarray()
+    sign, ld0 = np.linalg.slogdet(Ad)
+    assert abs(em.logdet() - ld0) < 1e-11 * abs(ld0)
+    B = rng.normal(size=(n, 6))
+    assert np.abs(Ad @ em.solve(B, mode=15) - B).max() < 1e-10 * np.abs(B).max()
+    Zq = em.selinv()
+    Zd = np.linalg.inv(Ad)
+    full = pat.to_csc(Zq).toarray()
+    mask = pat.to_csc(np.ones(pat.nslots * n)).toarray() != 0
+    assert np.abs(full[mask] - Zd[mask]).max() < 1e-10 * np.abs(Zd).max()
+
+
 def test_emulated_potrf_overlap_schedule(monkeypatch):
     """Opt-in factor schedule with the left-looking update split into its diagonal tile (main lane) and the rows below
     (side lane, LK_SYNC fork / join records): the launch list stays a valid serial order and gives the same factor."""
