@@ -203,7 +203,10 @@ class Emulator:
             src = self.sp[int(t["src_space"])]
             dst = self.sp[int(t["dst_space"])]
             ncp, ldd = int(t["ncp"]), int(t["ldd"])
-            dst[int(t["dst"]) + (ncp + ii) + (ncp + jj) * ldd] = src[int(t["src"]) + rel[ii] + rel[jj] * int(t["lds"])]
+            vals = src[int(t["src"]) + rel[ii] + rel[jj] * int(t["lds"])]
+            dst[int(t["dst"]) + (ncp + ii) + (ncp + jj) * ldd] = vals
+            if int(tr["ti"]) != int(tr["tj"]):      # k_selinv_gather reads the tiles on and below the diagonal and mirrors them
+                dst[int(t["dst"]) + (ncp + jj) + (ncp + ii) * ldd] = vals
 
     def _wtw(self, P, L):
         for t in P.wtw[L["task0"]:L["task0"] + L["ntasks"]]:

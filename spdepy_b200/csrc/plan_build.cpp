@@ -440,7 +440,7 @@ void Plan::build_selinv_program()
                 P.gather.push_back(g);
                 const int nt = (x.nr + 31) / 32;
                 for (int tj = 0; tj < nt; tj++)
-                    for (int ti = 0; ti < nt; ti++) P.tiles.push_back(TileRef{id, ti, tj, 0});
+                    for (int ti = tj; ti < nt; ti++) P.tiles.push_back(TileRef{id, ti, tj, 0});      // (the kernel mirrors)
             }
             L.ntasks = (int)(P.gather.size() - L.task0);
             L.ntiles = (int)(P.tiles.size() - L.tile0);

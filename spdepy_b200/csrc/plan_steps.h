@@ -460,7 +460,7 @@ static inline void push_gather_task(Program &P, Launch &L, long long dst, int ld
     P.gather.push_back(g);
     const int nt = (nr + 31) / 32;
     for (int tj = 0; tj < nt; tj++)
-        for (int ti = 0; ti < nt; ti++) P.tiles.push_back(TileRef{id, ti, tj, 0});
+        for (int ti = tj; ti < nt; ti++) P.tiles.push_back(TileRef{id, ti, tj, 0});      // (tiles on and below the diagonal: the kernel mirrors)
 }
 
 // Dense partial Cholesky of one front (panel already assembled): left-looking GEMM inside an outer block of
